@@ -1,0 +1,419 @@
+// capi.cu -- the extern "C" surface declared in include/swb200.h.
+#include "engine.h"
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cstring>
+
+namespace swb {
+const char *last_error_cstr();
+}
+using namespace swb;
+
+template <class T>
+__global__ void fill_kernel(T *p, T v, size_t n)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x)
+        p[q] = v;
+}
+
+
+extern "C" {
+
+const char *swb_last_error(void) { return last_error_cstr(); }
+int32_t swb_abi_version(void) { return SWB_ABI_VERSION; }
+
+int32_t swb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10)
+            ++ok;
+    }
+    return ok;
+}
+
+int64_t swb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+// ---- 1. device buffers --------------------------------------------------------------------------
+int32_t swb_set_device(int32_t device)
+{
+    SWB_API_BEGIN
+    SWB_CUDA(cudaSetDevice(device));
+    SWB_API_END
+}
+
+int32_t swb_malloc(void **dev_ptr, size_t nbytes)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(dev_ptr != nullptr, "null output pointer");
+    *dev_ptr = nullptr;
+    if (nbytes == 0)
+        return SWB_OK;
+    cudaError_t e = cudaMalloc(dev_ptr, nbytes);
+    if (e != cudaSuccess)
+        throw Error(e == cudaErrorMemoryAllocation ? SWB_ERR_NOMEM : SWB_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    SWB_CUDA(cudaMemset(*dev_ptr, 0, nbytes));
+    SWB_API_END
+}
+
+int32_t swb_free(void *dev_ptr)
+{
+    SWB_API_BEGIN
+    if (dev_ptr)
+        SWB_CUDA(cudaFree(dev_ptr));
+    SWB_API_END
+}
+
+int32_t swb_memcpy_h2d(void *dst, const void *src, size_t nbytes)
+{
+    SWB_API_BEGIN
+    if (nbytes)
+        SWB_CUDA(cudaMemcpy(dst, src, nbytes, cudaMemcpyHostToDevice));
+    SWB_API_END
+}
+
+int32_t swb_memcpy_d2h(void *dst, const void *src, size_t nbytes)
+{
+    SWB_API_BEGIN
+    if (nbytes)
+        SWB_CUDA(cudaMemcpy(dst, src, nbytes, cudaMemcpyDeviceToHost));
+    SWB_API_END
+}
+
+int32_t swb_memcpy_d2d(void *dst, const void *src, size_t nbytes)
+{
+    SWB_API_BEGIN
+    if (nbytes)
+        SWB_CUDA(cudaMemcpy(dst, src, nbytes, cudaMemcpyDeviceToDevice));
+    SWB_API_END
+}
+
+int32_t swb_fill(void *dev_ptr, int32_t dtype, double value, size_t first, size_t count)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(dtype == SWB_F32 || dtype == SWB_F64, "dtype must be SWB_F32 or SWB_F64");
+    if (count) {
+        unsigned blocks = (unsigned)std::min<size_t>((count + 255) / 256, 148u * 32u);
+        if (dtype == SWB_F64)
+            fill_kernel<double><<<blocks, 256>>>((double *)dev_ptr + first, value, count);
+        else
+            fill_kernel<float><<<blocks, 256>>>((float *)dev_ptr + first, (float)value, count);
+        check_launch("fill");
+        count_launch();
+    }
+    SWB_API_END
+}
+
+int32_t swb_synchronize(void)
+{
+    SWB_API_BEGIN
+    SWB_CUDA(cudaDeviceSynchronize());
+    SWB_API_END
+}
+
+// ---- 2. backend-module functions ------------------------------------------------------------------
+int32_t swb_acou_cd_forward_onestep(const swb_acou_cd_step_args *a)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(a != nullptr, "null argument struct");
+    cd_step(*a, a->rec.n > 0 && a->rec.tf != nullptr);
+    SWB_API_END
+}
+
+int32_t swb_acou_cd_adjoint_onestep(const swb_acou_cd_step_args *a)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(a != nullptr, "null argument struct");
+    cd_step(*a, false);
+    SWB_API_END
+}
+
+int32_t swb_acou_cd_correlate_gradient(int32_t dtype, int32_t flags, size_t ncells, void *grad, const void *adjcur, const void *p_itm2,
+                                       const void *p_itm1, const void *p_it, double dt, void *stream)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(dtype == SWB_F32 || dtype == SWB_F64, "dtype must be SWB_F32 or SWB_F64");
+    cd_correlate(dtype, flags, ncells, grad, adjcur, p_itm2, p_itm1, p_it, dt, (cudaStream_t)stream);
+    SWB_API_END
+}
+
+int32_t swb_prescale_residuals(int32_t dtype, int32_t ndim, const int64_t *n, void *residuals, int64_t nt, int64_t nrec, const int64_t *posrecs,
+                               const void *fact, void *stream)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(dtype == SWB_F32 || dtype == SWB_F64, "dtype must be SWB_F32 or SWB_F64");
+    SWB_REQUIRE(ndim >= 1 && ndim <= 3, "ndim must be 1..3");
+    prescale_residuals(dtype, ndim, n, residuals, nt, nrec, posrecs, fact, (cudaStream_t)stream);
+    SWB_API_END
+}
+
+int32_t swb_acou_vd_forward_onestep(const swb_acou_vd_step_args *a)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(a != nullptr, "null argument struct");
+    vd_step(*a, false);
+    SWB_API_END
+}
+
+int32_t swb_acou_vd_adjoint_onestep(const swb_acou_vd_step_args *a)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(a != nullptr, "null argument struct");
+    vd_step(*a, true);
+    SWB_API_END
+}
+
+int32_t swb_acou_vd_correlate_gradient_m0(int32_t dtype, int32_t, size_t ncells, void *grad_m0, const void *adjp, const void *p_it,
+                                          const void *p_itm1, double dt, void *stream)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(dtype == SWB_F32 || dtype == SWB_F64, "dtype must be SWB_F32 or SWB_F64");
+    vd_correlate_m0(dtype, ncells, grad_m0, adjp, p_it, p_itm1, dt, (cudaStream_t)stream);
+    SWB_API_END
+}
+
+int32_t swb_acou_vd_correlate_gradient_m1(int32_t dtype, int32_t flags, const int64_t *n, const double *spacing, void *const grad_m1_stag[2],
+                                          const void *const adjv[2], const void *p_it, void *stream)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(dtype == SWB_F32 || dtype == SWB_F64, "dtype must be SWB_F32 or SWB_F64");
+    vd_correlate_m1(dtype, flags, n, spacing, grad_m1_stag, adjv, p_it, (cudaStream_t)stream);
+    SWB_API_END
+}
+
+int32_t swb_ela_forward_onestep(const swb_ela_step_args *a)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(a != nullptr, "null argument struct");
+    ela_step(*a, false);
+    SWB_API_END
+}
+
+int32_t swb_ela_adjoint_onestep(const swb_ela_step_args *a)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(a != nullptr, "null argument struct");
+    ela_step(*a, true);
+    SWB_API_END
+}
+
+int32_t swb_ela_correlate_gradients(const swb_ela_correlate_args *a)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(a != nullptr, "null argument struct");
+    ela_correlate(*a);
+    SWB_API_END
+}
+
+// ---- 3. per-shot engine -----------------------------------------------------------------------------
+int32_t swb_sim_create(const swb_sim_desc *desc, swb_sim **sim)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(desc != nullptr && sim != nullptr, "null argument");
+    *sim = nullptr;
+    SimBase *impl = nullptr;
+    switch (desc->kind) {
+    case SWB_ACOU_CD:
+        impl = make_acoustic_cd(*desc);
+        break;
+    case SWB_ACOU_VD:
+        impl = make_acoustic_vd(*desc);
+        break;
+    case SWB_ELA_ISO:
+        impl = make_elastic_iso(*desc);
+        break;
+    default:
+        throw Error(SWB_ERR_ARG, "unknown simulation kind");
+    }
+    swb_sim *s = new swb_sim;
+    s->impl.reset(impl);
+    *sim = s;
+    SWB_API_END
+}
+
+int32_t swb_sim_destroy(swb_sim *sim)
+{
+    SWB_API_BEGIN
+    delete sim;
+    SWB_API_END
+}
+
+int64_t swb_sim_device_bytes(const swb_sim *sim) { return sim ? sim->impl->device_bytes() : 0; }
+
+#define SIM_CALL(expr)                                        \
+    SWB_API_BEGIN                                             \
+    SWB_REQUIRE(sim != nullptr && sim->impl, "null sim");    \
+    expr;                                                     \
+    SWB_API_END
+
+int32_t swb_sim_set_material(swb_sim *sim, int32_t nfields, const void *const *host_fields, int32_t interp)
+{
+    SIM_CALL(sim->impl->set_material(nfields, host_fields, interp, false))
+}
+int32_t swb_sim_set_material_device(swb_sim *sim, int32_t nfields, const void *const *dev_fields, int32_t interp)
+{
+    SIM_CALL(sim->impl->set_material(nfields, dev_fields, interp, true))
+}
+int32_t swb_sim_set_cpml(swb_sim *sim, int32_t axis, const void *a, const void *a_h, const void *b, const void *b_h)
+{
+    SIM_CALL(sim->impl->set_cpml(axis, a, a_h, b, b_h))
+}
+int32_t swb_sim_bind_scalar_shot(swb_sim *sim, int64_t nsrc, const int64_t *possrcs, const void *srctf, int64_t nrec, const int64_t *posrecs)
+{
+    SIM_CALL(sim->impl->bind_scalar_shot(nsrc, possrcs, srctf, nrec, posrecs))
+}
+int32_t swb_sim_bind_elastic_shot(swb_sim *sim, int32_t src_kind, const swb_sinc_points_host src_pts[2], const void *srctf, const void *Mxx,
+                                  const void *Mzz, const void *Mxz, const swb_sinc_points_host rec_pts[2])
+{
+    SIM_CALL(sim->impl->bind_elastic_shot(src_kind, src_pts, srctf, Mxx, Mzz, Mxz, rec_pts))
+}
+int32_t swb_sim_forward(swb_sim *sim, void *host_seismograms, int32_t snapevery) { SIM_CALL(sim->impl->forward(host_seismograms, snapevery)) }
+int32_t swb_sim_get_snapshot(swb_sim *sim, int64_t it, int32_t field, void *host_out) { SIM_CALL(sim->impl->get_snapshot(it, field, host_out)) }
+int32_t swb_sim_gradient_forward(swb_sim *sim, void *host_seismograms) { SIM_CALL(sim->impl->gradient_forward(host_seismograms)) }
+int32_t swb_sim_gradient_adjoint(swb_sim *sim, const void *host_adjsrc) { SIM_CALL(sim->impl->gradient_adjoint(host_adjsrc)) }
+int32_t swb_sim_gradient_l2(swb_sim *sim, const void *host_observed, void *host_seismograms_or_null, double *misfit_out)
+{
+    SIM_CALL(sim->impl->gradient_l2(host_observed, host_seismograms_or_null, misfit_out))
+}
+int32_t swb_sim_get_raw_gradient(swb_sim *sim, int32_t which, void *host_out) { SIM_CALL(sim->impl->get_raw_gradient(which, host_out)) }
+int32_t swb_sim_accumulate_gradient(swb_sim *sim, int64_t nsrcpos, const void *src_positions, int32_t mute_radius_src, int64_t nrecpos,
+                                    const void *rec_positions, int32_t mute_radius_rec)
+{
+    SIM_CALL(sim->impl->accumulate_gradient(nsrcpos, src_positions, mute_radius_src, nrecpos, rec_positions, mute_radius_rec))
+}
+int32_t swb_sim_zero_total_gradient(swb_sim *sim) { SIM_CALL(sim->impl->zero_total_gradient()) }
+int32_t swb_sim_total_gradient_ptr(swb_sim *sim, int32_t which, void **dev_ptr, size_t *nelem)
+{
+    SIM_CALL(sim->impl->total_gradient_ptr(which, dev_ptr, nelem))
+}
+int32_t swb_sim_get_total_gradient(swb_sim *sim, int32_t which, void *host_out) { SIM_CALL(sim->impl->get_total_gradient(which, host_out)) }
+int64_t swb_sim_cell_updates(const swb_sim *sim) { return sim ? sim->impl->cell_updates : 0; }
+int32_t swb_sim_get_field(swb_sim *sim, const char *name, void *host_out, size_t nbytes)
+{
+    SIM_CALL(sim->impl->get_field(std::string(name ? name : ""), host_out, nbytes))
+}
+int32_t swb_sim_stream(swb_sim *sim, void **stream_out) { SIM_CALL(*stream_out = (void *)sim->impl->stream) }
+int32_t swb_sim_kernel_timing(swb_sim *sim, int32_t enable, double *ms_total, int64_t *launches)
+{
+    SIM_CALL(sim->impl->kernel_timing(enable, ms_total, launches))
+}
+
+// ---- 4. multi-GPU (NCCL resolved at run time so that the library loads on hosts without it) ----------
+struct swb_comm {
+    ncclComm_t comm = nullptr;
+    int device = 0;
+    int nranks = 1, rank = 0;
+};
+
+namespace {
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi &nccl()
+{
+    static NcclApi api = [] {
+        NcclApi a;
+        a.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.h)
+            a.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (a.h) {
+            a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+            a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+            a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+            a.AllReduce = (decltype(a.AllReduce))dlsym(a.h, "ncclAllReduce");
+            a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+        }
+        return a;
+    }();
+    if (!api.h || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce)
+        throw Error(SWB_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    return api;
+}
+void nccl_check(ncclResult_t r, const char *what)
+{
+    if (r != ncclSuccess)
+        throw Error(SWB_ERR_NCCL, std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r) : "NCCL error"));
+}
+} // namespace
+
+int32_t swb_comm_unique_id(void *id128)
+{
+    SWB_API_BEGIN
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    nccl_check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(id128, &id, 128);
+    SWB_API_END
+}
+
+int32_t swb_comm_create(const void *id128, int32_t nranks, int32_t rank, int32_t device, swb_comm **comm)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(comm != nullptr && id128 != nullptr, "null argument");
+    SWB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+    SWB_CUDA(cudaSetDevice(device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    swb_comm *c = new swb_comm;
+    c->device = device;
+    c->nranks = nranks;
+    c->rank = rank;
+    ncclResult_t r = nccl().CommInitRank(&c->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        delete c;
+        nccl_check(r, "ncclCommInitRank");
+    }
+    *comm = c;
+    SWB_API_END
+}
+
+int32_t swb_comm_destroy(swb_comm *comm)
+{
+    SWB_API_BEGIN
+    if (comm) {
+        if (comm->comm)
+            nccl().CommDestroy(comm->comm);
+        delete comm;
+    }
+    SWB_API_END
+}
+
+int32_t swb_comm_allreduce_sum(swb_comm *comm, void *dev_ptr, size_t nelem, int32_t dtype, void *stream)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(comm != nullptr && comm->comm != nullptr, "null communicator");
+    SWB_REQUIRE(dtype == SWB_F32 || dtype == SWB_F64, "dtype must be SWB_F32 or SWB_F64");
+    SWB_CUDA(cudaSetDevice(comm->device));
+    nccl_check(nccl().AllReduce(dev_ptr, dev_ptr, nelem, dtype == SWB_F64 ? ncclDouble : ncclFloat, ncclSum, comm->comm, (cudaStream_t)stream),
+               "ncclAllReduce");
+    SWB_API_END
+}
+
+int32_t swb_sim_allreduce_total_gradient(swb_sim *sim, swb_comm *comm)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(sim != nullptr && sim->impl && comm != nullptr && comm->comm != nullptr, "null argument");
+    sim->impl->use_device();
+    for (int k = 0; k < sim->impl->n_total_gradients(); ++k) {
+        void *p;
+        size_t n;
+        sim->impl->total_gradient_ptr(k, &p, &n);
+        nccl_check(nccl().AllReduce(p, p, n, sim->impl->desc.dtype == SWB_F64 ? ncclDouble : ncclFloat, ncclSum, comm->comm, sim->impl->stream),
+                   "ncclAllReduce");
+    }
+    SWB_CUDA(cudaStreamSynchronize(sim->impl->stream));
+    SWB_API_END
+}
+
+} // extern "C"

@@ -1,0 +1,166 @@
+// engine.h -- per-shot engine objects behind swb_sim (one WaveSimulation on one GPU).
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+#include <map>
+#include <memory>
+#include <vector>
+
+namespace swb {
+
+// RAII device allocation, zero-filled
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept
+    {
+        if (this != &o) {
+            release();
+            p = o.p;
+            bytes = o.bytes;
+            o.p = nullptr;
+            o.bytes = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t b, cudaStream_t st = 0);
+    void release();
+    template <class T>
+    T *as() const { return (T *)p; }
+};
+
+extern std::atomic<long long> g_device_bytes;
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident checkpoint storage with the schedule of the reference's LinearCheckpointer
+// (src/utils/checkpointers.jl:1-107): a checkpoint of every registered field at each multiple of
+// check_freq (width-w fields also at the w-1 preceding steps), plus a rolling buffer of
+// check_freq+1 copies of the buffered fields that holds the segment being correlated.
+// A "field" is a list of component arrays (ScalarVariableField = 1, MultiVariableField = n).
+// ------------------------------------------------------------------------------------------------
+class DeviceCheckpointer {
+  public:
+    struct FieldSpec {
+        std::vector<size_t> comp_bytes;
+        int width = 1;
+        bool buffered = false;
+    };
+    DeviceCheckpointer(int64_t nt, int64_t check_freq, std::vector<FieldSpec> fields, cudaStream_t st);
+    void reset() { curr_ = last_; }
+    // savecheckpoint! (checkpointers.jl:44-56)
+    void save(int f, const std::vector<const void *> &comps, int64_t it);
+    bool is_saved(int f, int64_t it) const { return is_buffered(f, it) || is_checkpointed(f, it); }
+    bool is_buffered(int f, int64_t it) const { return fields_[f].buffered && curr_ <= it && it <= curr_ + cf_; }
+    bool is_checkpointed(int f, int64_t it) const { return slots_[f].count(it) != 0; }
+    // getsaved (checkpointers.jl:80-85): checkpoint storage preferred over the buffer
+    std::vector<void *> get(int f, int64_t it) const;
+    // initrecover! (checkpointers.jl:87-94)
+    void init_recover();
+    // the body of recover! for one re-forwarded step (checkpointers.jl:96-105)
+    void store_recovered(int f, const std::vector<const void *> &comps, int64_t it);
+    int64_t curr() const { return curr_; }
+    int64_t last() const { return last_; }
+    int64_t check_freq() const { return cf_; }
+    size_t bytes() const { return bytes_; }
+
+  private:
+    std::vector<void *> slot_ptrs(int f, int64_t slot) const;
+    std::vector<void *> buf_ptrs(int f, int64_t k) const;
+    int64_t nt_, cf_, last_, curr_;
+    std::vector<FieldSpec> fields_;
+    std::vector<std::map<int64_t, int64_t>> slots_; // per field: it -> slot index
+    std::vector<std::vector<DevBuf>> slabs_;        // per field, per component: all checkpoint slots
+    std::vector<std::vector<DevBuf>> bufslabs_;     // per field, per component: cf+1 buffer slots
+    cudaStream_t st_;
+    size_t bytes_ = 0;
+};
+
+// pinned host staging buffer
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~PinnedBuf();
+    void ensure(size_t b);
+};
+
+// ------------------------------------------------------------------------------------------------
+class SimBase {
+  public:
+    explicit SimBase(const swb_sim_desc &d);
+    virtual ~SimBase();
+    const swb_sim_desc desc;
+    cudaStream_t stream = nullptr;
+    size_t esize;
+    int64_t cell_updates = 0;
+    size_t ncells() const
+    {
+        size_t c = 1;
+        for (int d = 0; d < desc.ndim; ++d)
+            c *= (size_t)desc.n[d];
+        return c;
+    }
+    void use_device() const { SWB_CUDA(cudaSetDevice(desc.device)); }
+
+    virtual void set_material(int nfields, const void *const *fields, int interp, bool on_device) = 0;
+    void set_cpml(int axis, const void *a, const void *a_h, const void *b, const void *b_h);
+    virtual void bind_scalar_shot(int64_t nsrc, const int64_t *possrcs, const void *srctf, int64_t nrec, const int64_t *posrecs);
+    virtual void bind_elastic_shot(int src_kind, const swb_sinc_points_host src_pts[2], const void *srctf, const void *Mxx, const void *Mzz,
+                                   const void *Mxz, const swb_sinc_points_host rec_pts[2]);
+    virtual void forward(void *host_seis, int snapevery) = 0;
+    virtual void gradient_forward(void *host_seis) = 0;
+    virtual void gradient_adjoint(const void *host_adjsrc) = 0;
+    virtual void gradient_l2(const void *host_obs, void *host_seis, double *misfit) = 0;
+    virtual void get_raw_gradient(int which, void *host_out) = 0;
+    virtual void accumulate_gradient(int64_t nsrcpos, const void *srcpos, int rs, int64_t nrecpos, const void *recpos, int rr) = 0;
+    virtual int n_total_gradients() const = 0;
+    virtual void get_field(const std::string &name, void *host_out, size_t nbytes) = 0;
+    void zero_total_gradient();
+    void total_gradient_ptr(int which, void **p, size_t *nelem);
+    void get_total_gradient(int which, void *host_out);
+    void get_snapshot(int64_t it, int field, void *host_out);
+    void kernel_timing(int enable, double *ms_total, int64_t *launches);
+    int64_t device_bytes() const { return dev_bytes_; }
+
+  protected:
+    DevBuf dalloc(size_t bytes);
+    void upload(void *dst, const void *src, size_t bytes);
+    void download(void *dst, const void *src, size_t bytes);
+    void d2d(void *dst, const void *src, size_t bytes);
+    void zero(DevBuf &b);
+    void sync() { SWB_CUDA(cudaStreamSynchronize(stream)); }
+    swb_cpml_axis cpml_axis(int ax) const;
+    // timing of the dominant (stencil) kernel
+    void tic();
+    void toc();
+
+    DevBuf cpml_[3][4]; // a, a_h, b, b_h per axis
+    bool cpml_set_[3] = {false, false, false};
+    // acoustic shot binding
+    DevBuf possrc_, posrec_, srctf_, traces_, adjsrc_;
+    int64_t nsrc_ = 0, nrec_ = 0;
+    bool shot_bound_ = false;
+    bool fwd_done_ = false;
+    std::vector<DevBuf> total_grad_;
+    std::map<int64_t, std::vector<std::vector<char>>> snapshots_; // it -> field components on the host
+    PinnedBuf pin_;
+    int64_t dev_bytes_ = 0;
+    bool timing_ = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev_;
+    double t_ms_ = 0;
+    int64_t t_n_ = 0;
+};
+
+SimBase *make_acoustic_cd(const swb_sim_desc &d);
+SimBase *make_acoustic_vd(const swb_sim_desc &d);
+SimBase *make_elastic_iso(const swb_sim_desc &d);
+
+} // namespace swb
+
+struct swb_sim {
+    std::unique_ptr<swb::SimBase> impl;
+};

@@ -1,0 +1,431 @@
+// engine_core.cu -- device memory, checkpoint storage and the parts of the per-shot engine that do not
+// depend on the physics.
+#include "engine.h"
+#include <algorithm>
+#include <cstring>
+#include <cmath>
+
+namespace swb {
+
+std::atomic<long long> g_launches{0};
+std::atomic<long long> g_device_bytes{0};
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string &msg) { t_last_error = msg; }
+const char *last_error_cstr() { return t_last_error.c_str(); }
+
+// ---- Fornberg (1998) finite-difference weights ---------------------------------------------------
+// Same algorithm the reference uses to build its stencils (src/utils/fdgen.jl:11-47): weights of the
+// m-th derivative at 0 on the nodes x[0..n], computed with the published recurrence in double.
+static std::vector<double> fornberg_weights(std::vector<double> x, int m)
+{
+    std::sort(x.begin(), x.end());
+    const int np = (int)x.size();
+    std::vector<std::vector<double>> c(np, std::vector<double>(m + 1, 0.0));
+    double c1 = 1.0, c4 = x[0];
+    c[0][0] = 1.0;
+    for (int i = 1; i < np; ++i) {
+        const int mn = std::min(i, m);
+        double c2 = 1.0;
+        const double c5 = c4;
+        c4 = x[i];
+        for (int j = 0; j < i; ++j) {
+            const double c3 = x[i] - x[j];
+            c2 = c2 * c3;
+            if (j == i - 1) {
+                for (int k = mn; k >= 1; --k)
+                    c[i][k] = c1 * (k * c[i - 1][k - 1] - c5 * c[i - 1][k]) / c2;
+                c[i][0] = -c1 * c5 * c[i - 1][0] / c2;
+            }
+            for (int k = mn; k >= 1; --k)
+                c[j][k] = (c4 * c[j][k] - k * c[j][k - 1]) / c3;
+            c[j][0] = c4 * c[j][0] / c3;
+        }
+        c1 = c2;
+    }
+    std::vector<double> w(np);
+    for (int i = 0; i < np; ++i)
+        w[i] = c[i][m];
+    return w;
+}
+
+static std::vector<double> fd_coeffs(int deriv, int order)
+{
+    const int nnn = order + deriv - 1;
+    std::vector<double> nodes(nnn);
+    for (int k = 1; k <= nnn; ++k)
+        nodes[k - 1] = k - (nnn / 2.0 + 0.5);
+    return fornberg_weights(nodes, deriv);
+}
+
+const FdWeights &fd_weights()
+{
+    static const FdWeights w = [] {
+        FdWeights f{};
+        auto a = fd_coeffs(1, 2), b = fd_coeffs(2, 2), c = fd_coeffs(1, 4);
+        std::copy(a.begin(), a.end(), f.d1o2);
+        std::copy(b.begin(), b.end(), f.d2o2);
+        std::copy(c.begin(), c.end(), f.d1o4);
+        return f;
+    }();
+    return w;
+}
+
+// ---- DevBuf -----------------------------------------------------------------------------------------
+void DevBuf::alloc(size_t b, cudaStream_t st)
+{
+    release();
+    if (b == 0)
+        return;
+    cudaError_t e = cudaMalloc(&p, b);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        throw Error(e == cudaErrorMemoryAllocation ? SWB_ERR_NOMEM : SWB_ERR_CUDA,
+                    std::string("cudaMalloc of ") + std::to_string(b) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    bytes = b;
+    g_device_bytes.fetch_add((long long)b);
+    SWB_CUDA(cudaMemsetAsync(p, 0, b, st));
+}
+
+void DevBuf::release()
+{
+    if (p) {
+        cudaFree(p);
+        g_device_bytes.fetch_sub((long long)bytes);
+    }
+    p = nullptr;
+    bytes = 0;
+}
+
+PinnedBuf::~PinnedBuf()
+{
+    if (p)
+        cudaFreeHost(p);
+}
+void PinnedBuf::ensure(size_t b)
+{
+    if (b <= bytes)
+        return;
+    if (p)
+        cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+    SWB_CUDA(cudaMallocHost(&p, b));
+    bytes = b;
+}
+
+// ---- DeviceCheckpointer -----------------------------------------------------------------------------
+DeviceCheckpointer::DeviceCheckpointer(int64_t nt, int64_t cf, std::vector<FieldSpec> fields, cudaStream_t st)
+    : nt_(nt), cf_(cf), fields_(std::move(fields)), st_(st)
+{
+    SWB_REQUIRE(cf >= 1, "check_freq must be positive");
+    SWB_REQUIRE(cf < nt, "Checkpointing frequency must be smaller than the number of timesteps!");
+    last_ = (nt / cf) * cf;
+    curr_ = last_;
+    const int nf = (int)fields_.size();
+    slots_.resize(nf);
+    slabs_.resize(nf);
+    bufslabs_.resize(nf);
+    for (int f = 0; f < nf; ++f) {
+        // slots for it in 0..nt+1 with it % cf == 0, and the width-1 preceding steps (checkpointers.jl:22-34)
+        for (int64_t it = 0; it <= nt + 1; ++it)
+            if (it % cf == 0)
+                for (int64_t itw = it; itw > it - fields_[f].width; --itw)
+                    if (!slots_[f].count(itw)) {
+                        int64_t idx = (int64_t)slots_[f].size();
+                        slots_[f][itw] = idx;
+                    }
+        const size_t nslots = slots_[f].size();
+        for (size_t cb : fields_[f].comp_bytes) {
+            DevBuf b;
+            b.alloc(cb * nslots, st_);
+            bytes_ += b.bytes;
+            slabs_[f].push_back(std::move(b));
+            DevBuf bb;
+            if (fields_[f].buffered) {
+                bb.alloc(cb * (size_t)(cf + 1), st_);
+                bytes_ += bb.bytes;
+            }
+            bufslabs_[f].push_back(std::move(bb));
+        }
+    }
+}
+
+std::vector<void *> DeviceCheckpointer::slot_ptrs(int f, int64_t slot) const
+{
+    std::vector<void *> out;
+    for (size_t c = 0; c < fields_[f].comp_bytes.size(); ++c)
+        out.push_back((char *)slabs_[f][c].p + fields_[f].comp_bytes[c] * (size_t)slot);
+    return out;
+}
+
+std::vector<void *> DeviceCheckpointer::buf_ptrs(int f, int64_t k) const
+{
+    std::vector<void *> out;
+    for (size_t c = 0; c < fields_[f].comp_bytes.size(); ++c)
+        out.push_back((char *)bufslabs_[f][c].p + fields_[f].comp_bytes[c] * (size_t)k);
+    return out;
+}
+
+void DeviceCheckpointer::save(int f, const std::vector<const void *> &comps, int64_t it)
+{
+    const FieldSpec &fs = fields_[f];
+    bool ck = false;
+    for (int64_t itw = it; itw < it + fs.width; ++itw)
+        if (((itw % cf_) + cf_) % cf_ == 0)
+            ck = true;
+    if (ck) {
+        auto s = slots_[f].find(it);
+        SWB_REQUIRE(s != slots_[f].end(), "checkpoint slot missing");
+        auto dst = slot_ptrs(f, s->second);
+        for (size_t c = 0; c < comps.size(); ++c)
+            if (fs.comp_bytes[c])
+                SWB_CUDA(cudaMemcpyAsync(dst[c], comps[c], fs.comp_bytes[c], cudaMemcpyDeviceToDevice, st_));
+    }
+    if (fs.buffered && it >= last_) {
+        auto dst = buf_ptrs(f, it - last_);
+        for (size_t c = 0; c < comps.size(); ++c)
+            if (fs.comp_bytes[c])
+                SWB_CUDA(cudaMemcpyAsync(dst[c], comps[c], fs.comp_bytes[c], cudaMemcpyDeviceToDevice, st_));
+    }
+}
+
+std::vector<void *> DeviceCheckpointer::get(int f, int64_t it) const
+{
+    auto s = slots_[f].find(it);
+    if (s != slots_[f].end())
+        return slot_ptrs(f, s->second);
+    if (!is_buffered(f, it))
+        throw Error(SWB_ERR_STATE, "checkpointer: requested step is neither checkpointed nor buffered");
+    return buf_ptrs(f, it - curr_);
+}
+
+void DeviceCheckpointer::init_recover()
+{
+    const int64_t old = curr_;
+    curr_ -= cf_;
+    for (int f = 0; f < (int)fields_.size(); ++f) {
+        if (!fields_[f].buffered)
+            continue;
+        auto b0 = buf_ptrs(f, 0), bl = buf_ptrs(f, cf_);
+        auto c0 = slot_ptrs(f, slots_[f].at(curr_)), c1 = slot_ptrs(f, slots_[f].at(old));
+        for (size_t c = 0; c < fields_[f].comp_bytes.size(); ++c) {
+            SWB_CUDA(cudaMemcpyAsync(b0[c], c0[c], fields_[f].comp_bytes[c], cudaMemcpyDeviceToDevice, st_));
+            SWB_CUDA(cudaMemcpyAsync(bl[c], c1[c], fields_[f].comp_bytes[c], cudaMemcpyDeviceToDevice, st_));
+        }
+    }
+}
+
+void DeviceCheckpointer::store_recovered(int f, const std::vector<const void *> &comps, int64_t it)
+{
+    // buffers[name][it - start_rec_it + 2] with start_rec_it = curr+1 (1-based) == slot it - curr (0-based)
+    auto dst = buf_ptrs(f, it - curr_);
+    for (size_t c = 0; c < comps.size(); ++c)
+        SWB_CUDA(cudaMemcpyAsync(dst[c], comps[c], fields_[f].comp_bytes[c], cudaMemcpyDeviceToDevice, st_));
+}
+
+// ---- SimBase ----------------------------------------------------------------------------------------
+SimBase::SimBase(const swb_sim_desc &d) : desc(d), esize(d.dtype == SWB_F64 ? 8 : 4)
+{
+    SWB_REQUIRE(d.dtype == SWB_F32 || d.dtype == SWB_F64, "dtype must be SWB_F32 or SWB_F64");
+    SWB_REQUIRE(d.nt > 0, "Number of timesteps must be positive!");
+    SWB_REQUIRE(d.dt > 0, "Timestep size must be positive!");
+    SWB_REQUIRE(d.halo >= 0, "CPML halo size must be non-negative!");
+    for (int k = 0; k < d.ndim; ++k) {
+        SWB_REQUIRE(d.n[k] > 0, "All numbers of grid points must be positive!");
+        SWB_REQUIRE(d.spacing[k] > 0, "All grid spacings must be positive!");
+        SWB_REQUIRE(d.n[k] >= 2 * (int64_t)d.halo + 3, "Number grid points in the dimensions with C-PML boundaries must be at least 2*halo+3!");
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw Error(SWB_ERR_CUDA, "no CUDA device available: libswb200 has no CPU fallback");
+    SWB_REQUIRE(d.device >= 0 && d.device < ndev, "device index out of range");
+    SWB_CUDA(cudaSetDevice(d.device));
+    SWB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (int ax = 0; ax < d.ndim; ++ax) {
+        cpml_[ax][0] = dalloc(esize * 2 * (size_t)(d.halo + 1)); // a
+        cpml_[ax][1] = dalloc(esize * 2 * (size_t)d.halo);       // a_h
+        cpml_[ax][2] = dalloc(esize * 2 * (size_t)(d.halo + 1)); // b
+        cpml_[ax][3] = dalloc(esize * 2 * (size_t)d.halo);       // b_h
+    }
+}
+
+SimBase::~SimBase()
+{
+    cudaSetDevice(desc.device);
+    if (stream) {
+        cudaStreamSynchronize(stream);
+        cudaStreamDestroy(stream);
+    }
+    for (auto &e : tev_) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+}
+
+DevBuf SimBase::dalloc(size_t bytes)
+{
+    DevBuf b;
+    b.alloc(bytes, stream);
+    dev_bytes_ += (int64_t)bytes;
+    return b;
+}
+
+void SimBase::upload(void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0)
+        return;
+    // pageable source: the runtime stages it; synchronous w.r.t. the host buffer, ordered on our stream
+    SWB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    SWB_CUDA(cudaStreamSynchronize(stream));
+}
+
+void SimBase::download(void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0)
+        return;
+    SWB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaStreamSynchronize(stream));
+}
+
+void SimBase::d2d(void *dst, const void *src, size_t bytes)
+{
+    if (bytes)
+        SWB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream));
+}
+
+void SimBase::zero(DevBuf &b)
+{
+    if (b.bytes)
+        SWB_CUDA(cudaMemsetAsync(b.p, 0, b.bytes, stream));
+}
+
+void SimBase::set_cpml(int axis, const void *a, const void *a_h, const void *b, const void *b_h)
+{
+    use_device();
+    SWB_REQUIRE(axis >= 0 && axis < desc.ndim, "CPML axis out of range");
+    upload(cpml_[axis][0].p, a, cpml_[axis][0].bytes);
+    upload(cpml_[axis][1].p, a_h, cpml_[axis][1].bytes);
+    upload(cpml_[axis][2].p, b, cpml_[axis][2].bytes);
+    upload(cpml_[axis][3].p, b_h, cpml_[axis][3].bytes);
+    cpml_set_[axis] = true;
+}
+
+swb_cpml_axis SimBase::cpml_axis(int ax) const
+{
+    swb_cpml_axis c;
+    c.a = cpml_[ax][0].p;
+    c.a_h = cpml_[ax][1].p;
+    c.b = cpml_[ax][2].p;
+    c.b_h = cpml_[ax][3].p;
+    return c;
+}
+
+void SimBase::bind_scalar_shot(int64_t nsrc, const int64_t *possrcs, const void *srctf, int64_t nrec, const int64_t *posrecs)
+{
+    use_device();
+    SWB_REQUIRE(desc.kind == SWB_ACOU_CD || desc.kind == SWB_ACOU_VD, "scalar shots belong to acoustic simulations");
+    SWB_REQUIRE(nsrc > 0, "There must be at least one source!");
+    SWB_REQUIRE(nrec > 0, "There must be at least one receiver!");
+    for (int64_t s = 0; s < nsrc; ++s)
+        for (int d = 0; d < desc.ndim; ++d)
+            SWB_REQUIRE(possrcs[s + d * nsrc] >= 1 && possrcs[s + d * nsrc] <= desc.n[d], "source position outside the grid");
+    for (int64_t r = 0; r < nrec; ++r)
+        for (int d = 0; d < desc.ndim; ++d)
+            SWB_REQUIRE(posrecs[r + d * nrec] >= 1 && posrecs[r + d * nrec] <= desc.n[d], "receiver position outside the grid");
+    nsrc_ = nsrc;
+    nrec_ = nrec;
+    possrc_ = dalloc(sizeof(int64_t) * nsrc * desc.ndim);
+    posrec_ = dalloc(sizeof(int64_t) * nrec * desc.ndim);
+    srctf_ = dalloc(esize * desc.nt * nsrc);
+    traces_ = dalloc(esize * desc.nt * nrec);
+    if (desc.gradient)
+        adjsrc_ = dalloc(esize * desc.nt * nrec);
+    upload(possrc_.p, possrcs, possrc_.bytes);
+    upload(posrec_.p, posrecs, posrec_.bytes);
+    upload(srctf_.p, srctf, srctf_.bytes);
+    shot_bound_ = true;
+    fwd_done_ = false;
+}
+
+void SimBase::bind_elastic_shot(int, const swb_sinc_points_host *, const void *, const void *, const void *, const void *, const swb_sinc_points_host *)
+{
+    throw Error(SWB_ERR_ARG, "elastic shots belong to elastic simulations");
+}
+
+void SimBase::zero_total_gradient()
+{
+    use_device();
+    for (auto &b : total_grad_)
+        zero(b);
+}
+
+void SimBase::total_gradient_ptr(int which, void **p, size_t *nelem)
+{
+    SWB_REQUIRE(which >= 0 && which < (int)total_grad_.size(), "gradient component out of range");
+    *p = total_grad_[which].p;
+    *nelem = total_grad_[which].bytes / esize;
+}
+
+void SimBase::get_total_gradient(int which, void *host_out)
+{
+    use_device();
+    SWB_REQUIRE(which >= 0 && which < (int)total_grad_.size(), "gradient component out of range");
+    download(host_out, total_grad_[which].p, total_grad_[which].bytes);
+}
+
+void SimBase::get_snapshot(int64_t it, int field, void *host_out)
+{
+    auto s = snapshots_.find(it);
+    SWB_REQUIRE(s != snapshots_.end(), "no snapshot stored for this time step");
+    SWB_REQUIRE(field >= 0 && field < (int)s->second.size(), "snapshot field out of range");
+    std::memcpy(host_out, s->second[field].data(), s->second[field].size());
+}
+
+void SimBase::tic()
+{
+    if (!timing_)
+        return;
+    cudaEvent_t a, b;
+    SWB_CUDA(cudaEventCreate(&a));
+    SWB_CUDA(cudaEventCreate(&b));
+    SWB_CUDA(cudaEventRecord(a, stream));
+    tev_.push_back({a, b});
+}
+
+void SimBase::toc()
+{
+    if (!timing_ || tev_.empty())
+        return;
+    SWB_CUDA(cudaEventRecord(tev_.back().second, stream));
+}
+
+void SimBase::kernel_timing(int enable, double *ms_total, int64_t *launches)
+{
+    use_device();
+    SWB_CUDA(cudaStreamSynchronize(stream));
+    for (auto &e : tev_) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) {
+            t_ms_ += ms;
+            t_n_ += 1;
+        }
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    tev_.clear();
+    if (ms_total)
+        *ms_total = t_ms_;
+    if (launches)
+        *launches = t_n_;
+    if (enable == 0 || enable == 1) {
+        if ((enable == 1) != timing_) {
+            t_ms_ = 0;
+            t_n_ = 0;
+        }
+        timing_ = enable == 1;
+    }
+}
+
+} // namespace swb

@@ -1,0 +1,195 @@
+"""GPU parity tests for the acoustic hot path: CUDA engine (through the C ABI) vs the CPU oracle on identical
+seeded inputs.  Tolerances are the north-star ones (rel-L2 <= 1e-5 Float64, 1e-4 Float32); the
+reference-faithful arithmetic paths are additionally expected to agree to ~1 ulp per step, which the
+tight bounds below pin."""
+import numpy as np
+import pytest
+
+from cases import (acoustic_case, make_observed, oracle_forward, oracle_gradient, product_inputs, rel_l2, tol)
+
+pytestmark = pytest.mark.gpu
+
+
+def _forward_product(case, **kw):
+    import swb200 as S
+
+    params, matprop, shots, _, runparams, _ = product_inputs(case, **kw)
+    snaps = S.swforward(params, matprop, shots, runparams=runparams)
+    return [s.recs.seismograms for s in shots], snaps
+
+
+def _gradient_product(case, observed, **kw):
+    import swb200 as S
+
+    params, matprop, shots, misfit, runparams, gradparams = product_inputs(case, observed=observed, **kw)
+    res = S.swgradient(params, matprop, shots, misfit, runparams=runparams, gradparams=gradparams)
+    return res, [s.recs.seismograms for s in shots]
+
+
+FWD_CASES = [
+    ("acoustic_cd", (64, 56), np.float64, True),
+    ("acoustic_cd", (64, 56), np.float64, False),
+    ("acoustic_cd", (61, 53), np.float32, True),
+    ("acoustic_cd", (30, 26, 28), np.float64, True),
+    ("acoustic_cd", (30, 26, 28), np.float32, False),
+    ("acoustic_vd", (64, 56), np.float64, True),
+    ("acoustic_vd", (64, 56), np.float64, False),
+    ("acoustic_vd", (67, 59), np.float32, True),
+]
+
+
+@pytest.mark.parametrize("kind,n,dtype,freetop", FWD_CASES)
+@pytest.mark.parametrize("fused", [False, True])
+def test_forward_seismograms_match_oracle(kind, n, dtype, freetop, fused):
+    halo = 6 if len(n) == 3 else 8
+    case = acoustic_case(kind=kind, n=n, nt=150 if len(n) == 2 else 60, halo=halo, freetop=freetop, dtype=dtype, seed=len(n) * 7 + int(freetop))
+    ref, _ = oracle_forward(case)
+    got, _ = _forward_product(case, fused=fused)
+    for r, g in zip(ref, got):
+        assert g.dtype == np.dtype(dtype)
+        assert np.max(np.abs(r)) > 0
+        err = rel_l2(g, r)
+        assert err <= tol(dtype), err
+        # reference-faithful arithmetic: expect agreement to rounding level, far below the tolerance
+        assert err <= (1e-12 if dtype == np.float64 else 1e-6), err
+
+
+def test_forward_fast_f32_within_tolerance():
+    case = acoustic_case(kind="acoustic_vd", n=(96, 80), nt=300, halo=10, dtype=np.float32, seed=5)
+    ref, _ = oracle_forward(case)
+    got, _ = _forward_product(case, fast_f32=True)
+    for r, g in zip(ref, got):
+        assert rel_l2(g, r) <= tol(np.float32)
+    case = acoustic_case(kind="acoustic_cd", n=(96, 80), nt=300, halo=10, dtype=np.float32, seed=6)
+    ref, _ = oracle_forward(case)
+    got, _ = _forward_product(case, fast_f32=True)
+    for r, g in zip(ref, got):
+        assert rel_l2(g, r) <= tol(np.float32)
+
+
+GRAD_CASES = [
+    ("acoustic_cd", (48, 44), np.float64, 1),
+    ("acoustic_cd", (48, 44), np.float64, 7),
+    ("acoustic_cd", (48, 44), np.float64, 10),   # nt % check_freq == 0
+    ("acoustic_cd", (48, 44), np.float32, 9),
+    ("acoustic_cd", (24, 22, 26), np.float64, 6),
+    ("acoustic_vd", (48, 44), np.float64, 1),
+    ("acoustic_vd", (48, 44), np.float64, 7),
+    ("acoustic_vd", (48, 44), np.float64, 10),
+    ("acoustic_vd", (51, 47), np.float32, 9),
+]
+
+
+@pytest.mark.parametrize("kind,n,dtype,check_freq", GRAD_CASES)
+@pytest.mark.parametrize("fused", [False, True])
+def test_gradient_and_misfit_match_oracle(kind, n, dtype, check_freq, fused):
+    halo = 5 if len(n) == 3 else 6
+    nt = 100 if len(n) == 2 else 50
+    case = acoustic_case(kind=kind, n=n, nt=nt, halo=halo, dtype=dtype, seed=11 + check_freq)
+    syn, _ = oracle_forward(case)
+    observed = make_observed(case, syn)
+    (gref, mref), sref, _ = oracle_gradient(case, observed, check_freq=check_freq, mute_src=3, mute_rec=2)
+    (ggot, mgot), sgot = _gradient_product(case, observed, check_freq=check_freq, mute_src=3, mute_rec=2, fused=fused)
+    assert set(ggot) == set(gref)
+    for k in gref:
+        assert np.max(np.abs(gref[k])) > 0
+        err = rel_l2(ggot[k], gref[k])
+        assert err <= tol(dtype), (k, err)
+        assert err <= (1e-11 if dtype == np.float64 else 2e-5), (k, err)
+    assert abs(float(mgot) - float(mref)) <= tol(dtype) * abs(float(mref))
+    for r, g in zip(sref, sgot):
+        assert rel_l2(g, r) <= tol(dtype)
+
+
+@pytest.mark.parametrize("kind", ["acoustic_cd", "acoustic_vd"])
+def test_gradient_host_misfit_path_windows_and_diag_invcov(kind):
+    """pluggable-misfit path (forward -> host adjoint source -> adjoint) with windows and a diagonal covariance"""
+    case = acoustic_case(kind=kind, n=(48, 44), nt=100, halo=6, dtype=np.float64, seed=3, windows=True, diag_invcov=True)
+    syn, _ = oracle_forward(case)
+    observed = make_observed(case, syn)
+    (gref, mref), _, _ = oracle_gradient(case, observed, check_freq=8)
+    (ggot, mgot), _ = _gradient_product(case, observed, check_freq=8)
+    for k in gref:
+        assert rel_l2(ggot[k], gref[k]) <= 1e-11
+    assert abs(float(mgot) - float(mref)) <= 1e-10 * abs(float(mref))
+
+
+def test_vd_harmonic_interpolation_gradient():
+    case = acoustic_case(kind="acoustic_vd", n=(48, 44), nt=90, halo=6, dtype=np.float64, seed=21)
+    syn, _ = oracle_forward(case)
+    observed = make_observed(case, syn)
+    (gref, _), _, _ = oracle_gradient(case, observed, check_freq=9, interp_method="harmonic")
+    (ggot, _), _ = _gradient_product(case, observed, check_freq=9, interp_method="harmonic")
+    for k in gref:
+        assert rel_l2(ggot[k], gref[k]) <= 1e-10, k
+
+
+def test_checkpointed_equals_non_checkpointed_gradient():
+    """reference test: test/test_gradient_acoustic_constant_density.jl:194-312 (check_freq = floor(sqrt(nt)))"""
+    case = acoustic_case(kind="acoustic_cd", n=(64, 60), nt=144, halo=8, dtype=np.float64, seed=2)
+    syn, _ = oracle_forward(case)
+    observed = make_observed(case, syn)
+    (g1, m1), _ = _gradient_product(case, observed, check_freq=1)
+    (g2, m2), _ = _gradient_product(case, observed, check_freq=12)
+    assert np.array_equal(g1["vp"], g2["vp"])  # re-forwarding is deterministic: bit-identical
+    assert m1 == m2
+
+
+def test_snapshots_match_oracle():
+    case = acoustic_case(kind="acoustic_cd", n=(48, 44), nt=60, halo=6, dtype=np.float64, seed=4, nshots=1)
+    _, snaps_ref = oracle_forward(case, snapevery=20)
+    _, snaps = _forward_product(case, snapevery=20)
+    assert sorted(snaps[0].keys()) == [20, 40, 60]
+    for it in (20, 40, 60):
+        assert rel_l2(snaps[0][it]["pcur"], snaps_ref[0][it]) <= 1e-12
+
+
+def test_example_c1_full_size():
+    """BASELINE config 1: examples/simple_example_acoustic.jl verbatim (300x280, F64, nt=1500, 3 shots, free top,
+    mute 5/2, check_freq=1) -- seismograms, misfit and gradient against the oracle."""
+    import swb200 as S
+    from oracle import oracle as O
+
+    nt, dt, nx, nz, dh = 1500, 0.001, 300, 280, 8.0
+    velmod = np.zeros((nx, nz), order="F")
+    velmod[:, :] = 2000.0 + 12.0 * np.arange(nz)[None, :]
+    t = np.arange(nt) * dt
+    ixsrc = np.round(np.linspace(32, nx - 31, 3)).astype(int)
+    ixrec = np.round(np.linspace(30, nx - 29, 10)).astype(int)
+    f0 = 12.0
+    stf = (1000.0 * O.rickerstf(t, 1.20 / f0, f0)).reshape(nt, 1)
+    posrecs = np.zeros((10, 2))
+    posrecs[:, 0] = (ixrec - 1) * dh
+    posrecs[:, 1] = 2 * dh
+
+    def mkshots_product():
+        out = []
+        for i in range(3):
+            ps = np.array([[(ixsrc[i] - 1) * dh, (nz - 40) * dh]])
+            out.append(S.ScalarShot(srcs=S.ScalarSources(ps, stf.copy(), f0), recs=S.ScalarReceivers(posrecs.copy(), nt)))
+        return out
+
+    def mkshots_oracle():
+        return [O.ScalarShot(src_positions=np.array([[(ixsrc[i] - 1) * dh, (nz - 40) * dh]]), src_tf=np.asfortranarray(stf.copy()), domfreq=f0,
+                             rec_positions=posrecs.copy()) for i in range(3)]
+
+    bc = S.CPMLBoundaryConditionParameters(halo=20, rcoef=0.0001, freeboundtop=True)
+    params = S.InputParametersAcoustic(nt, dt, (nx, nz), (dh, dh), bc)
+    rp = S.RunParameters(parall="B200")
+    shots = mkshots_product()
+    S.swforward(params, S.VpAcousticCDMaterialProperties(velmod), shots, runparams=rp)
+    oparams = O.Params(nt=nt, dt=dt, gridsize=(nx, nz), spacing=(dh, dh), halo=20, rcoef=0.0001, freetop=True)
+    oshots = mkshots_oracle()
+    O.swforward(O.build_wavesim("acoustic_cd", oparams), [velmod], oshots)
+    for a, b in zip(shots, oshots):
+        assert rel_l2(a.recs.seismograms, b.seismograms) <= 1e-12
+    newvel = velmod - 0.2
+    newvel[29:40, 32:44] *= 0.9
+    observed = [s.recs.seismograms.copy(order="F") for s in shots]
+    gp = S.GradParameters(mute_radius_src=5, mute_radius_rec=2, compute_misfit=True)
+    grad, mis = S.swgradient(params, S.VpAcousticCDMaterialProperties(newvel), shots, [S.L2Misfit(observed=o) for o in observed], runparams=rp, gradparams=gp)
+    osim = O.build_wavesim("acoustic_cd", oparams, gradient=True, check_freq=1)
+    ograd, omis = O.swgradient(osim, [np.asfortranarray(newvel)], oshots, [O.L2Misfit(observed=o) for o in observed], mute_radius_src=5, mute_radius_rec=2,
+                               compute_misfit=True)
+    assert rel_l2(grad["vp"], ograd["vp"]) <= 1e-10
+    assert abs(mis - omis) <= 1e-10 * abs(omis)

@@ -1,0 +1,110 @@
+"""CPU-only checks of the product's host side and of the C-ABI library (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import swb200 as S
+
+    lib = S._lib.load()
+    header = open(os.path.join(ROOT, "include", "swb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(swb_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    assert sorted(S._lib.EXPORTS) == declared
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.swb_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import swb200 as S
+
+    if S.device_count() > 0:
+        pytest.skip("a device is present")
+    bc = S.CPMLBoundaryConditionParameters(halo=5)
+    params = S.InputParametersAcoustic(50, 1e-3, (40, 40), (10.0, 10.0), bc)
+    with pytest.raises(RuntimeError):
+        S.build_wavesim(params, S.VpAcousticCDMaterialProperties(2000.0 * np.ones((40, 40))), runparams=S.RunParameters())
+    with pytest.raises(ValueError):
+        S.build_wavesim(params, S.VpAcousticCDMaterialProperties(2000.0 * np.ones((40, 40))), runparams=S.RunParameters(parall="threads"))
+    # a raw engine call must fail with a CUDA error, not silently succeed
+    lib = S._lib.load()
+    d = S._lib.swb_sim_desc(kind=1, dtype=1, ndim=2, device=0, dt=1e-3, nt=10, halo=2, freetop=1, gradient=0, check_freq=1)
+    d.n[0], d.n[1] = 16, 16
+    d.spacing[0], d.spacing[1] = 1.0, 1.0
+    h = C.c_void_p()
+    assert lib.swb_sim_create(C.byref(d), C.byref(h)) == 2  # SWB_ERR_CUDA
+    assert b"no CPU fallback" in lib.swb_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "seismicwaves.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".jl")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "import oracle" not in src and "from oracle" not in src and "libswref" not in src, f
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("freetop", [True, False])
+def test_hostprep_cpml_matches_oracle(dtype, freetop):
+    import swb200 as S
+
+    T = np.dtype(dtype).type
+    ours = S.hostprep.init_bdc(T(3456.7), T(1.1e-3), 20, T(1e-4), (T(10.0), T(7.5)), freetop, T(12.0), dtype)
+    ref = O.init_bdc(T(3456.7), T(1.1e-3), 20, T(1e-4), (T(10.0), T(7.5)), freetop, T(12.0), dtype)
+    for (a, a_h, b, b_h), r in zip(ours, ref):
+        assert a.dtype == np.dtype(dtype) and len(a) == 42 and len(a_h) == 40
+        assert np.array_equal(a, r.a) and np.array_equal(a_h, r.a_h) and np.array_equal(b, r.b) and np.array_equal(b_h, r.b_h)
+    a, a_h, b, b_h = ours[-1]
+    if freetop:
+        assert np.all(a[:21] == 0) and np.all(b[:21] == 1) and np.all(a_h[:20] == 0) and np.all(b_h[:20] == 1)
+    assert np.all(b[21:] <= 1) and np.all(a[22:] < 0)
+    # halo = 0: no NaNs (cpmlcoeffs.jl:30-32)
+    z = S.hostprep.init_bdc(T(2000), T(1e-3), 0, T(1.0), (T(5.0),), False, T(5.0), dtype)[0]
+    assert len(z[0]) == 2 and len(z[1]) == 0 and np.all(np.isfinite(z[0])) and np.all(z[0] == 0)
+
+
+def test_hostprep_positions_and_scaling_match_oracle():
+    import swb200 as S
+
+    rng = np.random.default_rng(0)
+    for dtype in (np.float32, np.float64):
+        T = np.dtype(dtype).type
+        pos = rng.uniform(0, 500, size=(50, 2)).astype(dtype)
+        pos[0] = [15.0, 25.0]  # exact ties (x.5 in grid units) round up
+        a = S.hostprep.find_nearest_grid_points(pos, (T(10.0), T(10.0)), dtype)
+        b = O.find_nearest_grid_points(pos, (T(10.0), T(10.0)), dtype)
+        assert np.array_equal(a, b) and a.dtype == np.int64
+        assert list(a[0]) == [3, 4]
+    assert [list(r) for r in S.distribsrcs(10, 4)] == [list(r) for r in O.distribsrcs(10, 4)]
+
+
+def test_types_mirror_reference_checks():
+    import swb200 as S
+
+    with pytest.raises(AssertionError):
+        S.ScalarSources(np.zeros((2, 2)), np.zeros((10, 3)), 5.0)
+    with pytest.raises(AssertionError):
+        S.InputParametersAcoustic(0, 1e-3, (10, 10), (1.0, 1.0), S.CPMLBoundaryConditionParameters())
+    with pytest.raises(ValueError):
+        S.L2Misfit(observed=np.zeros(5))
+    with pytest.raises(AssertionError):
+        S.L2Misfit(observed=np.zeros((5, 2)), windows=[(0, 3)])
+    with pytest.raises(AssertionError):
+        S.GradParameters(check_freq=0)
+    m = S.L2Misfit(observed=np.zeros((5, 2)))
+    recs = S.ScalarReceivers(np.zeros((2, 2)), 5)
+    recs.seismograms[:] = 2.0
+    assert m.calcmisfit(recs) == 20.0
+    assert np.array_equal(m.dchi_du(recs), 2.0 * np.ones((5, 2)))

@@ -1,0 +1,182 @@
+"""Pins the CPU oracle with the reference's own known-answer tests (the reference ships no golden vectors):
+test/test_analytical_vs_numerical_acoustic_constant_density.jl, ..._variable_density.jl,
+test/test_forward_constant_density.jl (Float32 + receiver permutation), test/test_interpolations.jl,
+test/test_gradient_acoustic_*.jl (checkpointed == non-checkpointed)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from refsetups import analytical_cd, analytical_vd, setup_constant_vel_cpml, setup_constant_vel_rho_cpml, trapz
+
+C0, F0 = 1000.0, 5.0
+
+
+@pytest.fixture(autouse=True)
+def _omp():
+    O.use_openmp(True)  # same arithmetic, just faster; bit-reproducibility vs serial is checked below
+    yield
+    O.use_openmp(False)
+
+
+def _check_analytic(times, trace, Gc, dt, nt):
+    # test_analytical_vs_numerical_acoustic_constant_density.jl:38 -- 1 % integrated error bound
+    assert trace.shape == Gc.shape == (nt,)
+    assert trapz(times, np.abs(trace - Gc)) <= np.max(np.abs(Gc)) * 0.01 * (dt * nt)
+
+
+@pytest.mark.parametrize("nt,halo,rcoef", [(500, 0, 1.0), (1000, 20, 1e-4)])
+def test_cd_1d_analytic(nt, halo, rcoef):
+    dx = 2.5
+    dt = 0.99 * dx / C0
+    params, shots, _, vp = setup_constant_vel_cpml(nt, dt, (501,), (dx,), C0, F0, halo, rcoef)
+    O.swforward(O.build_wavesim("acoustic_cd", params), [vp], shots)
+    times, Gc = analytical_cd(1, C0, dt, nt, shots[0])
+    _check_analytic(times, shots[0].seismograms[:, 0], Gc, dt, nt)
+
+
+@pytest.mark.parametrize("nt,halo,rcoef,f", [(700, 0, 1.0, 1.0), (1400, 20, 1e-4, 0.99)])
+def test_cd_2d_analytic(nt, halo, rcoef, f):
+    # reference sizes are 801^2 (:66-95); 401^2 with the receiver distance kept is enough to pin the scheme here
+    dx = 2.5
+    n = 801 if halo == 0 else 801
+    dt = f * dx / C0 / np.sqrt(2)
+    params, shots, _, vp = setup_constant_vel_cpml(nt, dt, (n, n), (dx, dx), C0, F0, halo, rcoef)
+    O.swforward(O.build_wavesim("acoustic_cd", params), [vp], shots)
+    times, Gc = analytical_cd(2, C0, dt, nt, shots[0])
+    _check_analytic(times, shots[0].seismograms[:, 0], Gc, dt, nt)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("nt,halo,rcoef", [(200, 0, 1.0), (400, 20, 1e-4)])
+def test_cd_3d_analytic(nt, halo, rcoef):
+    d = 8.0
+    dt = 0.99 * d / C0 / np.sqrt(3)
+    params, shots, _, vp = setup_constant_vel_cpml(nt, dt, (121, 121, 121), (d, d, d), C0, F0, halo, rcoef)
+    O.swforward(O.build_wavesim("acoustic_cd", params), [vp], shots)
+    times, Gc = analytical_cd(3, C0, dt, nt, shots[0])
+    _check_analytic(times, shots[0].seismograms[:, 0], Gc, dt, nt)
+
+
+@pytest.mark.parametrize("N,nt,n,d,halo,rcoef", [(1, 500, (501,), (2.5,), 0, 1.0), (1, 5000, (501,), (2.5,), 20, 1e-4),
+                                                (2, 350, (401, 401), (5.0, 5.0), 0, 1.0), (2, 1400, (401, 401), (5.0, 5.0), 20, 1e-4)])
+def test_vd_analytic(N, nt, n, d, halo, rcoef):
+    rho0, t0 = 1500.0, 2 / F0
+    dt = 0.99 * d[0] / C0 * 6 / 7 if N == 1 else 0.99 * d[0] / C0 / np.sqrt(2) * 6 / 7
+    params, shots, _, vp, rho = setup_constant_vel_rho_cpml(nt, dt, n, d, C0, rho0, t0, F0, halo, rcoef)
+    O.swforward(O.build_wavesim("acoustic_vd", params), [vp, rho], shots)
+    times, Gc = analytical_vd(N, C0, rho0, dt, nt, t0, F0, shots[0])
+    _check_analytic(times, shots[0].seismograms[:, 0], Gc, dt, nt)
+
+
+def test_cd_1d_float32_analytic():
+    # test/test_forward_constant_density.jl:18-40
+    nt, dx = 1000, 2.5
+    dt = 0.99 * dx / C0
+    params, shots, _, vp = setup_constant_vel_cpml(nt, dt, (501,), (dx,), C0, F0, 20, 1e-4, dtype=np.float32)
+    O.swforward(O.build_wavesim("acoustic_cd", params), [vp.astype(np.float32)], shots)
+    assert shots[0].seismograms.dtype == np.float32
+    times, Gc = analytical_cd(1, C0, dt, nt, shots[0])
+    _check_analytic(times, shots[0].seismograms[:, 0].astype(np.float64), Gc, dt, nt)
+
+
+def test_receiver_permutation_symmetry_2d():
+    # test/test_forward_constant_density.jl:42-266 (Gaussian anomaly model; permuting receivers permutes the traces)
+    nt, n, dx = 300, 201, 2.5
+    dt = 0.99 * dx / 1300.0 / np.sqrt(2)
+    x = np.arange(1, n + 1)
+    sigma = 50 / 3
+    vp = 1000.0 + 300.0 * np.exp(-0.5 * ((x[:, None] - (n + 1) / 2) ** 2 + (x[None, :] - (n + 1) / 2) ** 2) / sigma**2)
+    vp = np.asfortranarray(vp)
+    params = O.Params(nt=nt, dt=dt, gridsize=(n, n), spacing=(dx, dx), halo=20, rcoef=1e-4, freetop=False)
+    L = (n - 1) * dx
+    times = np.arange(nt) * dt
+    tf = np.asfortranarray(O.rickerstf(times, 2 / F0, F0).reshape(nt, 1))
+    recs = np.array([[L / 3, L / 2], [L / 2, L / 3], [2 * L / 3, L / 2]])
+    perm = [2, 0, 1]
+    s1 = O.ScalarShot(src_positions=np.array([[L / 2, L / 2]]), src_tf=tf, domfreq=F0, rec_positions=recs)
+    s2 = O.ScalarShot(src_positions=np.array([[L / 2, L / 2]]), src_tf=tf, domfreq=F0, rec_positions=recs[perm])
+    O.swforward(O.build_wavesim("acoustic_cd", params), [vp], [s1, s2])
+    assert np.array_equal(s1.seismograms[:, perm], s2.seismograms)
+
+
+def test_omp_build_is_bit_identical_to_serial():
+    from cases import acoustic_case, oracle_forward
+
+    case = acoustic_case(kind="acoustic_vd", n=(40, 36), nt=60, halo=5, seed=9)
+    O.use_openmp(False)
+    a, _ = oracle_forward(case)
+    O.use_openmp(True)
+    b, _ = oracle_forward(case)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("kind", ["acoustic_cd", "acoustic_vd"])
+@pytest.mark.parametrize("n", [(101,), (60, 50)])
+def test_checkpointed_gradient_equals_full_storage(kind, n):
+    # test/test_gradient_acoustic_constant_density.jl:194-312, test_gradient_acoustic_variable_density.jl:93-179
+    from cases import acoustic_case, make_observed, oracle_forward, oracle_gradient
+
+    case = acoustic_case(kind=kind, n=n, nt=150, halo=8, freetop=False, seed=4)
+    syn, _ = oracle_forward(case)
+    obs = make_observed(case, syn)
+    (g1, m1), _, _ = oracle_gradient(case, obs, check_freq=1)
+    (g2, m2), _, sim = oracle_gradient(case, obs, check_freq=int(np.floor(np.sqrt(150))))
+    for k in g1:
+        assert np.max(np.abs(g1[k])) > 0
+        assert np.array_equal(g1[k], g2[k])
+    assert m1 == m2 and m1 > 0
+    assert sim.ckpt.n_refwd > 0
+
+
+def test_misfit_equals_swmisfit():
+    # test/test_gradient_acoustic_constant_density.jl:18-51 (misfit ≈ swmisfit!)
+    from cases import acoustic_case, case_params_oracle, make_observed, matprop_list, oracle_forward, oracle_gradient, oracle_shots
+
+    case = acoustic_case(kind="acoustic_cd", n=(60, 50), nt=120, halo=8, seed=8, nshots=1)
+    syn, _ = oracle_forward(case)
+    obs = make_observed(case, syn)
+    (_, m), _, _ = oracle_gradient(case, obs, check_freq=1)
+    sim = O.build_wavesim("acoustic_cd", case_params_oracle(case))
+    ms = O.swmisfit(sim, matprop_list(case), oracle_shots(case), [O.L2Misfit(observed=obs[0])])
+    assert m == pytest.approx(ms, rel=1e-14)
+
+
+def test_interpolations_exact_values():
+    # test/test_interpolations.jl:6-198
+    m = np.array([1.0, 2.0, 3.0, 4.0])
+    assert np.array_equal(O.interp("arithmetic", m, [0]), [1.5, 2.5, 3.5])
+    assert np.allclose(O.interp("harmonic", m, [0]), [1.333, 2.4, 3.428], atol=1e-3)
+    assert np.array_equal(O.dfdm("arithmetic", m, (slice(0, 3),), [0]), [0.5, 0.5, 0.5])
+    g = np.array([1 / m[0] + 1 / m[1], 1 / m[1] + 1 / m[2], 1 / m[2] + 1 / m[3]])
+    assert np.allclose(O.dfdm("harmonic", m, (slice(0, 3),), [0]), (-2 / g**2) * (-1 / m[:-1] ** 2), atol=1e-3)
+    assert np.allclose(O.dfdm("harmonic", m, (slice(1, 4),), [0]), (-2 / g**2) * (-1 / m[1:] ** 2), atol=1e-3)
+    gi = np.array([0.1, 0.2, 0.3])
+    exp = np.zeros(4)
+    exp[:-1] += gi * 0.5
+    exp[1:] += gi * 0.5
+    assert np.allclose(O.back_interp("arithmetic", m, gi, [0]), exp)
+    m2 = np.asfortranarray(np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0], [7.0, 8.0, 9.0]]))
+    assert np.array_equal(O.interp("arithmetic", m2, [0]), [[2.5, 3.5, 4.5], [5.5, 6.5, 7.5]])
+    assert np.array_equal(O.interp("arithmetic", m2, [1]), [[1.5, 2.5], [4.5, 5.5], [7.5, 8.5]])
+    assert np.array_equal(O.interp("arithmetic", m2, [0, 1]), [[3.0, 4.0], [6.0, 7.0]])
+    assert np.array_equal(O.dfdm("arithmetic", m2, (slice(0, 2), slice(0, 2)), [0, 1]), np.full((2, 2), 0.25))
+    g2 = np.asfortranarray(np.array([[0.1, 0.2], [0.3, 0.4]]))
+    exp2 = np.zeros((3, 3))
+    for di in (0, 1):
+        for dj in (0, 1):
+            exp2[di:di + 2, dj:dj + 2] += g2 * 0.25
+    assert np.allclose(O.back_interp("arithmetic", m2, g2, [0, 1]), exp2)
+
+
+def test_fd_coefficients():
+    # fdgen.jl:44-47 -- the classic staggered weights fall out of Fornberg's recurrence exactly
+    assert np.array_equal(O.fdcoeffs(1, 2), [-1.0, 1.0])
+    assert np.array_equal(O.fdcoeffs(2, 2), [1.0, -2.0, 1.0])
+    assert np.array_equal(O.fdcoeffs(1, 4), [1 / 24, -9 / 8, 9 / 8, -1 / 24])
+
+
+def test_distribsrcs():
+    # utils.jl:28-45
+    assert [list(r) for r in O.distribsrcs(10, 4)] == [[0, 1, 2], [3, 4, 5], [6, 7], [8, 9]]
+    assert [list(r) for r in O.distribsrcs(2, 4)] == [[0], [1]]
+    assert [list(r) for r in O.distribsrcs(64, 8)] == [list(range(8 * k, 8 * k + 8)) for k in range(8)]
