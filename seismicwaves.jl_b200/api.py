@@ -175,6 +175,11 @@ class WaveSimulation:
         _lib.check(self.lib.swb_sim_get_field(self._h, name.encode(), _vp(g), g.nbytes))
         return g
 
+    def dominant_kernel_name(self) -> str:
+        return self._dominant_kernel
+
+    _dominant_kernel = "step"
+
     def kernel_timing(self, enable: int) -> Tuple[float, int]:
         ms, n = C.c_double(), C.c_int64()
         _lib.check(self.lib.swb_sim_kernel_timing(self._h, enable, C.byref(ms), C.byref(n)))

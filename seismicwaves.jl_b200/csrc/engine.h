@@ -149,7 +149,8 @@ class SimBase {
     std::map<int64_t, std::vector<std::vector<char>>> snapshots_; // it -> field components on the host
     PinnedBuf pin_;
     int64_t dev_bytes_ = 0;
-    bool timing_ = false;
+    bool timing_ = false, tsampled_ = false;
+    int64_t tcount_ = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev_;
     double t_ms_ = 0;
     int64_t t_n_ = 0;

@@ -385,8 +385,10 @@ void SimBase::get_snapshot(int64_t it, int field, void *host_out)
 
 void SimBase::tic()
 {
-    if (!timing_)
+    tsampled_ = false;
+    if (!timing_ || (tcount_++ % 8) != 0) // sample every 8th step: keeps the event overhead out of the timed region
         return;
+    tsampled_ = true;
     cudaEvent_t a, b;
     SWB_CUDA(cudaEventCreate(&a));
     SWB_CUDA(cudaEventCreate(&b));
@@ -396,7 +398,7 @@ void SimBase::tic()
 
 void SimBase::toc()
 {
-    if (!timing_ || tev_.empty())
+    if (!timing_ || !tsampled_ || tev_.empty())
         return;
     SWB_CUDA(cudaEventRecord(tev_.back().second, stream));
 }
