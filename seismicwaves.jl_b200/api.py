@@ -297,6 +297,7 @@ class AcousticVDStaggeredCPMLWaveSimulation(_AcousticBase):
     grad_names = ("vp", "rho")
     _matprop_type = VpRhoAcousticVDMaterialProperties
     _cfl_factor = 7.0 / 6.0
+    _dominant_kernel = "vd_fused_kernel (v update + p update + inject + record [+ correlations], one launch per time step)"
 
     def set_wavesim_matprop(self, matprop) -> None:
         vp, rho = matprop.vp, matprop.rho

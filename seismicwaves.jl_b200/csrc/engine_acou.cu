@@ -6,6 +6,7 @@
 // stay on the device with the LinearCheckpointer schedule, and the host is only touched for
 // the seismograms and (optionally) the adjoint source.
 #include "engine.h"
+#include "vd_fused.h"
 #include <cstring>
 
 namespace swb {
@@ -343,7 +344,8 @@ SimBase *make_acoustic_cd(const swb_sim_desc &d) { return new AcousticCD(d); }
 // =====================================================================================================
 class AcousticVD : public SimBase {
   public:
-    explicit AcousticVD(const swb_sim_desc &d) : SimBase(d)
+    // own_state = false: a subclass keeps the wavefield state in its own layout (fused engine below)
+    explicit AcousticVD(const swb_sim_desc &d, bool own_state = true) : SimBase(d)
     {
         SWB_REQUIRE(d.ndim == 2, "acoustic variable-density engine supports N = 2");
         nx_ = d.n[0];
@@ -355,28 +357,33 @@ class AcousticVD : public SimBase {
         m0_ = dalloc(nb);
         m1_[0] = dalloc(nbx);
         m1_[1] = dalloc(nby);
-        p_ = dalloc(nb);
-        v_[0] = dalloc(nbx);
-        v_[1] = dalloc(nby);
         auto mem = [&](DevBuf(&psi)[2], DevBuf(&xi)[2]) {
             psi[0] = dalloc(esize * 2 * h * ny_);
             psi[1] = dalloc(esize * 2 * h * nx_);
             xi[0] = dalloc(esize * 2 * (h + 1) * ny_);
             xi[1] = dalloc(esize * 2 * (h + 1) * nx_);
         };
-        mem(psi_, xi_);
+        if (own_state) {
+            p_ = dalloc(nb);
+            v_[0] = dalloc(nbx);
+            v_[1] = dalloc(nby);
+            mem(psi_, xi_);
+        }
         if (d.gradient) {
             g0_ = dalloc(nb);
             g1s_[0] = dalloc(nbx);
             g1s_[1] = dalloc(nby);
             g1_ = dalloc(nb);
             work_ = dalloc(nb);
+            total_grad_.push_back(dalloc(nb));
+            total_grad_.push_back(dalloc(nb));
+            misfit_acc_ = dalloc(sizeof(double));
+        }
+        if (d.gradient && own_state) {
             ap_ = dalloc(nb);
             av_[0] = dalloc(nbx);
             av_[1] = dalloc(nby);
             mem(psi_adj_, xi_adj_);
-            total_grad_.push_back(dalloc(nb));
-            total_grad_.push_back(dalloc(nb));
             std::vector<DeviceCheckpointer::FieldSpec> fs(4);
             fs[0].comp_bytes = {nb};
             fs[0].buffered = true;                                   // "pcur", width 1
@@ -385,7 +392,6 @@ class AcousticVD : public SimBase {
             fs[3].comp_bytes = {xi_[0].bytes, xi_[1].bytes};         // "ξ"
             ckpt_.reset(new DeviceCheckpointer(d.nt, d.check_freq, fs, stream));
             dev_bytes_ += (int64_t)ckpt_->bytes();
-            misfit_acc_ = dalloc(sizeof(double));
         }
         sync();
     }
@@ -515,8 +521,8 @@ class AcousticVD : public SimBase {
         download(host_out, b->p, b->bytes);
     }
 
-  private:
-    void begin_shot()
+  protected:
+    virtual void begin_shot()
     {
         use_device();
         SWB_REQUIRE(mat_set_, "material properties not set");
@@ -615,7 +621,7 @@ class AcousticVD : public SimBase {
     }
 
     // acou_gradient.jl:141-176
-    void adjoint_loop()
+    virtual void adjoint_loop()
     {
         prescale_residuals(desc.dtype, 2, desc.n, adjsrc_.p, desc.nt, nrec_, posrec_.as<int64_t>(), m0_.p, stream);
         for (int64_t it = desc.nt; it >= 1; --it) {
@@ -645,7 +651,7 @@ class AcousticVD : public SimBase {
         sync();
     }
 
-    void take_snapshot(int64_t it)
+    virtual void take_snapshot(int64_t it)
     {
         std::vector<std::vector<char>> comps(3);
         const DevBuf *src[3] = {&p_, &v_[0], &v_[1]};
@@ -664,6 +670,15 @@ class AcousticVD : public SimBase {
     bool mat_set_ = false;
 };
 
-SimBase *make_acoustic_vd(const swb_sim_desc &d) { return new AcousticVD(d); }
+#include "engine_vd_fused.inc"
+
+SimBase *make_acoustic_vd(const swb_sim_desc &d)
+{
+    // the fused single-launch engine is the default; SWB_FLAG_NO_FUSION (or a grid smaller than one stencil)
+    // selects the one-launch-per-reference-kernel path
+    if (!(d.flags & SWB_FLAG_NO_FUSION) && d.n[0] >= 8 && d.n[1] >= 8)
+        return new AcousticVDFused(d);
+    return new AcousticVD(d);
+}
 
 } // namespace swb
