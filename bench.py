@@ -77,53 +77,55 @@ def n_refwd(nt: int, cf: int) -> int:
 # clocks sampling during the timed region (B200_PROFILING.md)
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / throttle-reason samples during the timed region, taken in-process through NVML (nvidia_ml_py).
+    A separate `nvidia-smi -lms` process perturbed the launch stream of the benchmark itself (driver lock contention:
+    the kernels here are ~100 us each and launched back to back), so the sampling is a light NVML poll every 250 ms."""
 
-    def __init__(self, device_index: int):
-        self.idx = device_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, device_index: int, period_s: float = 0.25):
+        self.idx, self.period = device_index, period_s
+        self.samples, self._stop, self.thr, self.err = [], threading.Event(), None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._read, daemon=True)
-            self.thr.start()
-        except OSError:
-            self.proc = None
+            import pynvml as N
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.idx
+            self.h = N.nvmlDeviceGetHandleByIndex(phys)
+            self.N = N
+        except Exception as e:  # noqa: BLE001
+            self.err = f"NVML unavailable: {e}"
+            return
+        self.thr = threading.Thread(target=self._run, daemon=True)
+        self.thr.start()
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
+    def _run(self):
+        N = self.N
+        while not self._stop.is_set():
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if f[4 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                sm = N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)
+                smax = N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+                reasons = N.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(N, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                power = N.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), sm, smax, power, int(reasons)))
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            self._stop.wait(self.period)
+
+    def stop(self, t_from=None, t_to=None):
+        self._stop.set()
+        if self.thr is not None:
+            self.thr.join(timeout=2)
+        sel = [x for x in self.samples if (t_from is None or x[0] >= t_from) and (t_to is None or x[0] <= t_to)]
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+        reasons = sorted(k for k, b in bits.items() if any(x[4] & b for x in sel))
+        return {"sm_mhz": float(np.median([x[1] for x in sel])), "sm_max_mhz": float(max(x[2] for x in sel)), "power_w_max": float(max(x[3] for x in sel)),
+                "samples": len(sel), "reasons": reasons, "how": "NVML poll every 250 ms during the timed region"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -291,14 +293,15 @@ def run_b200(args):
         S._lib.check(lib.swb_sim_accumulate_gradient(wavesim._h, sp.shape[0], S.api._vp(np.asfortranarray(sp)), gradparams.mute_radius_src,
                                                      rpp.shape[0], S.api._vp(np.asfortranarray(rpp)), gradparams.mute_radius_rec))
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # started before the warm-up so that nvidia-smi's start-up cost is not inside the timed region
     for w in range(args.warmup):
         one_step(w)
     wavesim.zero_total_gradient()
     wavesim.kernel_timing(1)
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
+    t_from = time.perf_counter()
     cu0, l0 = wavesim.cell_updates(), lib.swb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
@@ -309,10 +312,11 @@ def run_b200(args):
     e1.record(ext)
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_from, time.perf_counter()) if rank == 0 else None
     cu = wavesim.cell_updates() - cu0
     launches = lib.swb_launch_count() - l0
-    kt_ms, kt_n = wavesim.kernel_timing(0)
+    wavesim.kernel_timing(0)
+    (kt_ms, kt_n), (ka_ms, ka_n) = wavesim.kernel_timing_class(0), wavesim.kernel_timing_class(1)
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     tcu = torch.tensor([float(cu)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -364,7 +368,13 @@ def run_b200(args):
             ach = bytes_per_cell * n * n / dur / 1e9
             roof = {"bound": "hbm", "kernel": wavesim.dominant_kernel_name(), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                     "peak_source": peak_src, "frac_of_8TBs_nominal": ach / 8000.0, "avg_launch_us": dur * 1e6, "timed_launches": kt_n,
-                    "algorithmic_bytes_per_launch": bytes_per_cell * n * n}
+                    "algorithmic_bytes_per_launch": bytes_per_cell * n * n,
+                    "sampling": "CUDA events on the engine's stream around every 8th launch inside the timed region"}
+            if ka_n > 0:  # the adjoint launch: adjoint step + injection + three correlations, 17 arrays x 4 B per cell
+                dur_a = ka_ms / ka_n * 1e-3
+                ach_a = 17 * 4 * n * n / dur_a / 1e9
+                roof["adjoint_kernel"] = {"achieved": ach_a, "frac": ach_a / peak, "avg_launch_us": dur_a * 1e6, "timed_launches": ka_n,
+                                          "algorithmic_bytes_per_launch": 17 * 4 * n * n}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -405,7 +415,9 @@ def main():
     ap.add_argument("--grid", type=int, default=4096, help="override the grid size (non-headline runs only)")
     ap.add_argument("--nt", type=int, default=1000, help="override the number of time steps (non-headline runs only)")
     ap.add_argument("--check-freq", type=int, default=0)
-    ap.add_argument("--fast-f32", type=int, default=0, help="1 = pure Float32 arithmetic (SWB_FLAG_FAST_F32)")
+    ap.add_argument("--fast-f32", type=int, default=1,
+                    help="1 (default) = Float32 storage and Float32 arithmetic (SWB_FLAG_FAST_F32; within the 1e-4 Float32 tolerance); "
+                         "0 = Float64 intermediates, bit-faithful to the reference's promotion rule")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

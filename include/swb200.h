@@ -301,6 +301,8 @@ int32_t swb_sim_get_field(swb_sim *sim, const char *name, void *host_out, size_t
 int32_t swb_sim_stream(swb_sim *sim, void **stream_out);
 /* timing of the dominant kernel on the sim's own stream (CUDA events): accumulates while enabled */
 int32_t swb_sim_kernel_timing(swb_sim *sim, int32_t enable, double *ms_total, int64_t *launches);
+/* same totals split by launch class: 0 = forward / re-forward step, 1 = adjoint step (with the fused correlation) */
+int32_t swb_sim_kernel_timing_class(swb_sim *sim, int32_t cls, double *ms_total, int64_t *launches);
 
 /* ---------------------------------------------------------------------------------------------
  * 4. Multi-GPU: shots are sharded across ranks by the caller (distribsrcs, src/utils/utils.jl:28-45);

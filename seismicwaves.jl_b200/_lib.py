@@ -112,7 +112,7 @@ EXPORTS = [
     "swb_sim_bind_scalar_shot", "swb_sim_bind_elastic_shot", "swb_sim_forward", "swb_sim_get_snapshot",
     "swb_sim_gradient_forward", "swb_sim_gradient_adjoint", "swb_sim_gradient_l2", "swb_sim_get_raw_gradient",
     "swb_sim_accumulate_gradient", "swb_sim_zero_total_gradient", "swb_sim_total_gradient_ptr", "swb_sim_get_total_gradient",
-    "swb_sim_cell_updates", "swb_sim_get_field", "swb_sim_stream", "swb_sim_kernel_timing",
+    "swb_sim_cell_updates", "swb_sim_get_field", "swb_sim_stream", "swb_sim_kernel_timing", "swb_sim_kernel_timing_class",
     "swb_comm_unique_id", "swb_comm_create", "swb_comm_destroy", "swb_comm_allreduce_sum", "swb_sim_allreduce_total_gradient",
 ]
 
@@ -179,6 +179,7 @@ def load() -> C.CDLL:
         "swb_sim_get_field": [vp, C.c_char_p, vp, sz],
         "swb_sim_stream": [vp, C.POINTER(vp)],
         "swb_sim_kernel_timing": [vp, i32, C.POINTER(dbl), C.POINTER(i64)],
+        "swb_sim_kernel_timing_class": [vp, i32, C.POINTER(dbl), C.POINTER(i64)],
         "swb_comm_unique_id": [vp],
         "swb_comm_create": [vp, i32, i32, i32, C.POINTER(vp)],
         "swb_comm_destroy": [vp],

@@ -185,6 +185,11 @@ class WaveSimulation:
         _lib.check(self.lib.swb_sim_kernel_timing(self._h, enable, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    def kernel_timing_class(self, cls: int) -> Tuple[float, int]:
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(self.lib.swb_sim_kernel_timing_class(self._h, cls, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     # ---- per-shot drivers -------------------------------------------------------------------------------
     def set_wavesim_matprop(self, matprop) -> None:
         raise NotImplementedError

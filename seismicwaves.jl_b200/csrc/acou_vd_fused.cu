@@ -78,13 +78,44 @@ __device__ __forceinline__ CT fd4(const VdFusedParams<T> &P, T fm1, T f0, T f1, 
     return acc * (CT)inv;
 }
 
+// smem layout (elements of T); every input of the tile is staged with cp.async so that a CTA has its whole
+// working set (~57 KB in Float32) in flight at once -- the SM keeps HBM busy with 3 resident CTAs instead of
+// depending on per-thread load/use latency.
+template <class T, int TY, bool ADJ>
+struct VdSmem {
+    static constexpr int P_OFF = 0;                              // p_in   rows -3 .. TY+2, cols -8 .. TX+7
+    static constexpr int VX_OFF = P_OFF + (TY + 6) * SW;         // vx     rows  0 .. TY-1, cols -8 .. TX+7 (updated in place)
+    static constexpr int M1X_OFF = VX_OFF + TY * SW;             // m1x    same shape
+    static constexpr int VY_OFF = M1X_OFF + TY * SW;             // vy     rows -2 .. TY,   cols 0 .. TX-1   (updated in place)
+    static constexpr int M1Y_OFF = VY_OFF + (TY + 3) * TX;       // m1y    same shape
+    static constexpr int PI_OFF = M1Y_OFF + (TY + 3) * TX;       // p_it   rows -1 .. TY+1, cols -8 .. TX+7 (adjoint only)
+    static constexpr int TOTAL = PI_OFF + (ADJ ? (TY + 3) * SW : 0);
+};
+
+// stage `nrows` rows of chunks [c0, c1) (chunk 0 = global column gx0) from a padded plane into shared memory
+template <class T>
+__device__ __forceinline__ void stage_rows(T *dst, int dstride, const T *src_row0, long long ld, int gx0, int nrows, int c0, int c1, int tid)
+{
+    const int ncs = c1 - c0;
+    for (int idx = tid; idx < nrows * ncs; idx += NTHR) {
+        const int r = idx / ncs, c = c0 + (idx - r * ncs);
+        T *d = dst + r * dstride + 4 * c;
+        if (gx0 + 4 * c >= ld) { // beyond the row pitch: only feeds cells that are never stored
+            Chunk<T> z = {};
+            st_chunk(d, z);
+        } else
+            cp_async_chunk(d, src_row0 + (long long)r * ld + 4 * c);
+    }
+}
+
 template <class T, class CT, bool ADJ, int TY, bool edge>
 __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char *smem_raw)
 {
-    T *sp = reinterpret_cast<T *>(smem_raw);          // p_in      rows -3 .. TY+2, cols -8 .. TX+7
-    T *svx = sp + (TY + 6) * SW;                      // vx_new    rows  0 .. TY-1, cols -8 .. TX+7
-    T *svy = svx + TY * SW;                           // vy_new    rows -2 .. TY,   cols  0 .. TX-1
-    T *spi = svy + (TY + 3) * TX;                     // p_it      rows -1 .. TY+1, cols -8 .. TX+7 (adjoint only)
+    typedef VdSmem<T, TY, ADJ> L;
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    // sp / svx / sm1x / spi point at (row 0, column 0) of the tile; svy / sm1y at (row -2, column 0)
+    T *sp = sm + L::P_OFF + 3 * SW + 8, *svx = sm + L::VX_OFF + 8, *sm1x = sm + L::M1X_OFF + 8;
+    T *svy = sm + L::VY_OFF, *sm1y = sm + L::M1Y_OFF, *spi = sm + L::PI_OFF + SW + 8;
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
@@ -92,35 +123,21 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
     const long long ld = P.ld;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
 
-    // ---- phase 1: stage p_in (and p_it) in shared memory -------------------------------------------------
+    // ---- phase 1: stage every input of the tile in shared memory ------------------------------------------
     {
-        const T *g = P.p_in + (long long)(y0 - 3) * ld + (x0 - 8);
-        for (int idx = tid; idx < (TY + 6) * (NCH + 4); idx += NTHR) {
-            const int r = idx / (NCH + 4), c = idx - r * (NCH + 4);
-            const bool halo_row = r < 3 || r >= TY + 3;
-            if (halo_row && (c < 2 || c >= NCH + 2))
-                continue; // corners are never read
-            if (x0 - 8 + 4 * c >= ld) { // beyond the row pitch: only feeds cells that are never stored
-                Chunk<T> z = {};
-                st_chunk(sp + r * SW + 4 * c, z);
-                continue;
-            }
-            cp_async_chunk(sp + r * SW + 4 * c, g + (long long)r * ld + 4 * c);
+        const long long o = (long long)y0 * ld + x0;
+        // p_in: rows 0 .. TY-1 need columns -8 .. TX+7, the 3 halo rows above and below only columns 0 .. TX-1
+        stage_rows(sp, SW, P.p_in + o, ld, x0, TY, -2, NCH + 2, tid);
+        stage_rows(sp - 3 * SW, SW, P.p_in + o - 3 * ld, ld, x0, 3, 0, NCH, tid);
+        stage_rows(sp + TY * SW, SW, P.p_in + o + TY * ld, ld, x0, 3, 0, NCH, tid);
+        stage_rows(svx, SW, P.vx_in + o, ld, x0, TY, -1, NCH + 1, tid);
+        stage_rows(svy, TX, P.vy_in + o - 2 * ld, ld, x0, TY + 3, 0, NCH, tid);
+        if (P.do_v) {
+            stage_rows(sm1x, SW, P.m1x + o, ld, x0, TY, -1, NCH + 1, tid);
+            stage_rows(sm1y, TX, P.m1y + o - 2 * ld, ld, x0, TY + 3, 0, NCH, tid);
         }
-        if (ADJ) {
-            const T *gi = P.pc_it + (long long)(y0 - 1) * ld + (x0 - 8);
-            for (int idx = tid; idx < (TY + 3) * (NCH + 4); idx += NTHR) {
-                const int r = idx / (NCH + 4), c = idx - r * (NCH + 4);
-                if (c < 1 || c >= NCH + 3)
-                    continue;
-                if (x0 - 8 + 4 * c >= ld) {
-                    Chunk<T> z = {};
-                    st_chunk(spi + r * SW + 4 * c, z);
-                    continue;
-                }
-                cp_async_chunk(spi + r * SW + 4 * c, gi + (long long)r * ld + 4 * c);
-            }
-        }
+        if (ADJ)
+            stage_rows(spi - SW, SW, P.pc_it + o - ld, ld, x0, TY + 3, -1, NCH + 1, tid);
         cp_async_wait_all();
         __syncthreads();
     }
@@ -131,116 +148,112 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
         for (int e = e0 + tid; e < e1; e += NTHR) {
             const int cell = P.rec_cell[e];
             const int r = cell / TX, c = cell - r * TX;
-            P.traces[(size_t)P.rec_idx[e] * P.rec_nt + (P.rec_it - 1)] = sp[(r + 3) * SW + c + 8];
+            P.traces[(size_t)P.rec_idx[e] * P.rec_nt + (P.rec_it - 1)] = sp[r * SW + c];
         }
     }
 
-    // ---- phase 2a: vx_new on columns -4 .. TX+3 (chunks -1 .. NCH), rows 0 .. TY-1 ------------------------
-    for (int idx = tid; idx < TY * (NCH + 2); idx += NTHR) {
-        const int r = idx / (NCH + 2), c = idx - r * (NCH + 2) - 1;
-        const int gx = x0 + 4 * c, gy = y0 + r; // 0-based global column of the chunk's first cell / row
-        Chunk<T> out = {};
-        if (gx < ld) {
+    if (P.do_v) {
+        // ---- phase 2a: vx_new on columns -4 .. TX+3 (chunks -1 .. NCH), rows 0 .. TY-1 --------------------
+        for (int idx = tid; idx < TY * (NCH + 2); idx += NTHR) {
+            const int r = idx / (NCH + 2), c = idx - r * (NCH + 2) - 1;
+            const int gx = x0 + 4 * c, gy = y0 + r; // 0-based global column of the chunk's first cell / row
+            if (gx >= ld)
+                continue;
             const long long q = (long long)gy * ld + gx;
-            const Chunk<T> vin = ldg_chunk(P.vx_in + q);
-            out = vin;
-            if (P.do_v) {
-                const Chunk<T> m1 = ldg_chunk(P.m1x + q);
-                const T *ps = sp + (r + 3) * SW + 4 * c + 8; // p at column 4c
-                const Chunk<T> pa = ldg_chunk(ps - 4), pb = ldg_chunk(ps), pc = ldg_chunk(ps + 4);
-                const T w[7] = {pa.v[3], pb.v[0], pb.v[1], pb.v[2], pb.v[3], pc.v[0], pc.v[1]};
-                const bool owned = c >= 0 && c < NCH && gy < ny;
-                Chunk<T> g1 = {};
-                T wi[7];
-                if (ADJ && owned) {
-                    g1 = ldg_chunk(P.g1x + q);
-                    const T *pis = spi + (r + 1) * SW + 4 * c + 8;
-                    const Chunk<T> ia = ldg_chunk(pis - 4), ib = ldg_chunk(pis), ic = ldg_chunk(pis + 4);
-                    wi[0] = ia.v[3], wi[1] = ib.v[0], wi[2] = ib.v[1], wi[3] = ib.v[2], wi[4] = ib.v[3], wi[5] = ic.v[0], wi[6] = ic.v[1];
-                }
+            T *vs = svx + r * SW + 4 * c;
+            const Chunk<T> vin = ldg_chunk(vs);
+            const Chunk<T> m1 = ldg_chunk(sm1x + r * SW + 4 * c);
+            const T *ps = sp + r * SW + 4 * c; // p at column 4c
+            const Chunk<T> pa = ldg_chunk(ps - 4), pb = ldg_chunk(ps), pc = ldg_chunk(ps + 4);
+            const T w[7] = {pa.v[3], pb.v[0], pb.v[1], pb.v[2], pb.v[3], pc.v[0], pc.v[1]};
+            const bool owned = c >= 0 && c < NCH && gy < ny;
+            Chunk<T> out = vin, g1 = {};
+            T wi[7];
+            if (ADJ && owned) {
+                g1 = ldg_chunk(P.g1x + q);
+                const T *pis = spi + r * SW + 4 * c;
+                const Chunk<T> ia = ldg_chunk(pis - 4), ib = ldg_chunk(pis), ic = ldg_chunk(pis + 4);
+                wi[0] = ia.v[3], wi[1] = ib.v[0], wi[2] = ib.v[1], wi[3] = ib.v[2], wi[4] = ib.v[3], wi[5] = ic.v[0], wi[6] = ic.v[1];
+            }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int I = gx + e + 1, J = gy + 1; // 1-based reference indices
-                    if (edge && !(I >= 1 && I <= nx - 1 && J <= ny))
-                        continue; // outside update_vx_CPML!'s range: stays as it is (zero)
-                    CT D = fd4<T, CT>(P, w[e], w[e + 1], w[e + 2], w[e + 3], P.inv_dx);
-                    if (edge && (I <= h || I >= nx - h)) {
-                        const int ii = I <= h ? I : I - nx + 2 * h + 1;
-                        const size_t qs = (size_t)(J - 1) * (2 * h) + (ii - 1);
-                        T sn;
-                        D = cpml_apply<T, CT>(D, P.a_xh[ii - 1], P.b_xh[ii - 1], P.psi_x_in[qs], sn);
-                        if (owned)
-                            P.psi_x_out[qs] = sn;
-                    }
-                    out.v[e] = (T)((CT)vin.v[e] - (CT)m1.v[e] * D);
-                    if (ADJ && owned) {
-                        const CT Dc = fd4<T, CT>(P, wi[e], wi[e + 1], wi[e + 2], wi[e + 3], P.inv_dx);
-                        g1.v[e] = (T)((CT)g1.v[e] + (CT)out.v[e] * Dc);
-                    }
+            for (int e = 0; e < 4; ++e) {
+                const int I = gx + e + 1, J = gy + 1; // 1-based reference indices
+                if (edge && !(I >= 1 && I <= nx - 1 && J <= ny))
+                    continue; // outside update_vx_CPML!'s range: stays as it is (zero)
+                CT D = fd4<T, CT>(P, w[e], w[e + 1], w[e + 2], w[e + 3], P.inv_dx);
+                if (edge && (I <= h || I >= nx - h)) {
+                    const int ii = I <= h ? I : I - nx + 2 * h + 1;
+                    const size_t qs = (size_t)(J - 1) * (2 * h) + (ii - 1);
+                    T sn;
+                    D = cpml_apply<T, CT>(D, P.a_xh[ii - 1], P.b_xh[ii - 1], P.psi_x_in[qs], sn);
+                    if (owned)
+                        P.psi_x_out[qs] = sn;
                 }
-                if (owned) {
-                    st_chunk(P.vx_out + q, out);
-                    if (ADJ)
-                        st_chunk(P.g1x + q, g1);
+                out.v[e] = (T)((CT)vin.v[e] - (CT)m1.v[e] * D);
+                if (ADJ && owned) {
+                    const CT Dc = fd4<T, CT>(P, wi[e], wi[e + 1], wi[e + 2], wi[e + 3], P.inv_dx);
+                    g1.v[e] = (T)((CT)g1.v[e] + (CT)out.v[e] * Dc);
                 }
             }
+            st_chunk(vs, out);
+            if (owned) {
+                st_chunk(P.vx_out + q, out);
+                if (ADJ)
+                    st_chunk(P.g1x + q, g1);
+            }
         }
-        st_chunk(svx + r * SW + 4 * c + 8, out);
-    }
 
-    // ---- phase 2b: vy_new on rows -2 .. TY, columns 0 .. TX-1 ---------------------------------------------
-    for (int idx = tid; idx < (TY + 3) * NCH; idx += NTHR) {
-        const int rr = idx / NCH, c = idx - rr * NCH;
-        const int r = rr - 2;
-        const int gx = x0 + 4 * c, gy = y0 + r;
-        Chunk<T> out = {};
-        if (gx < ld) {
+        // ---- phase 2b: vy_new on rows -2 .. TY, columns 0 .. TX-1 -----------------------------------------
+        for (int idx = tid; idx < (TY + 3) * NCH; idx += NTHR) {
+            const int rr = idx / NCH, c = idx - rr * NCH;
+            const int r = rr - 2;
+            const int gx = x0 + 4 * c, gy = y0 + r;
+            if (gx >= ld)
+                continue;
             const long long q = (long long)gy * ld + gx;
-            const Chunk<T> vin = ldg_chunk(P.vy_in + q);
-            out = vin;
-            if (P.do_v) {
-                const Chunk<T> m1 = ldg_chunk(P.m1y + q);
-                const T *ps = sp + (r + 3) * SW + 4 * c + 8;
-                const Chunk<T> pa = ldg_chunk(ps - SW), pb = ldg_chunk(ps), pc = ldg_chunk(ps + SW), pd = ldg_chunk(ps + 2 * SW);
-                const bool owned = r >= 0 && r < TY && gy < ny;
-                Chunk<T> g1 = {}, ia = {}, ib = {}, ic = {}, id = {};
-                if (ADJ && owned) {
-                    g1 = ldg_chunk(P.g1y + q);
-                    const T *pis = spi + (r + 1) * SW + 4 * c + 8;
-                    ia = ldg_chunk(pis - SW), ib = ldg_chunk(pis), ic = ldg_chunk(pis + SW), id = ldg_chunk(pis + 2 * SW);
-                }
+            T *vs = svy + rr * TX + 4 * c;
+            const Chunk<T> vin = ldg_chunk(vs);
+            const Chunk<T> m1 = ldg_chunk(sm1y + rr * TX + 4 * c);
+            const T *ps = sp + r * SW + 4 * c;
+            const Chunk<T> pa = ldg_chunk(ps - SW), pb = ldg_chunk(ps), pc = ldg_chunk(ps + SW), pd = ldg_chunk(ps + 2 * SW);
+            const bool owned = r >= 0 && r < TY && gy < ny;
+            Chunk<T> out = vin, g1 = {}, ia = {}, ib = {}, ic = {}, id = {};
+            if (ADJ && owned) {
+                g1 = ldg_chunk(P.g1y + q);
+                const T *pis = spi + r * SW + 4 * c;
+                ia = ldg_chunk(pis - SW), ib = ldg_chunk(pis), ic = ldg_chunk(pis + SW), id = ldg_chunk(pis + 2 * SW);
+            }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int I = gx + e + 1, J = gy + 1;
-                    if (edge && !(I <= nx && J >= 1 && J <= ny - 1))
-                        continue;
-                    CT D = fd4<T, CT>(P, pa.v[e], pb.v[e], pc.v[e], pd.v[e], P.inv_dy);
-                    if (edge && (J <= h || J >= ny - h)) {
-                        const int jj = J <= h ? J : J - ny + 2 * h + 1;
-                        const size_t qs = (size_t)(jj - 1) * nx + (I - 1);
-                        T sn;
-                        D = cpml_apply<T, CT>(D, P.a_yh[jj - 1], P.b_yh[jj - 1], P.psi_y_in[qs], sn);
-                        if (owned)
-                            P.psi_y_out[qs] = sn;
-                    }
-                    out.v[e] = (T)((CT)vin.v[e] - (CT)m1.v[e] * D);
-                    if (ADJ && owned) {
-                        const CT Dc = fd4<T, CT>(P, ia.v[e], ib.v[e], ic.v[e], id.v[e], P.inv_dy);
-                        g1.v[e] = (T)((CT)g1.v[e] + (CT)out.v[e] * Dc);
-                    }
+            for (int e = 0; e < 4; ++e) {
+                const int I = gx + e + 1, J = gy + 1;
+                if (edge && !(I <= nx && J >= 1 && J <= ny - 1))
+                    continue;
+                CT D = fd4<T, CT>(P, pa.v[e], pb.v[e], pc.v[e], pd.v[e], P.inv_dy);
+                if (edge && (J <= h || J >= ny - h)) {
+                    const int jj = J <= h ? J : J - ny + 2 * h + 1;
+                    const size_t qs = (size_t)(jj - 1) * nx + (I - 1);
+                    T sn;
+                    D = cpml_apply<T, CT>(D, P.a_yh[jj - 1], P.b_yh[jj - 1], P.psi_y_in[qs], sn);
+                    if (owned)
+                        P.psi_y_out[qs] = sn;
                 }
-                if (owned) {
-                    st_chunk(P.vy_out + q, out);
-                    if (ADJ)
-                        st_chunk(P.g1y + q, g1);
+                out.v[e] = (T)((CT)vin.v[e] - (CT)m1.v[e] * D);
+                if (ADJ && owned) {
+                    const CT Dc = fd4<T, CT>(P, ia.v[e], ib.v[e], ic.v[e], id.v[e], P.inv_dy);
+                    g1.v[e] = (T)((CT)g1.v[e] + (CT)out.v[e] * Dc);
                 }
             }
+            st_chunk(vs, out);
+            if (owned) {
+                st_chunk(P.vy_out + q, out);
+                if (ADJ)
+                    st_chunk(P.g1y + q, g1);
+            }
         }
-        st_chunk(svy + rr * TX + 4 * c, out);
+        if (!P.do_p)
+            return;
+        __syncthreads();
     }
-    if (!P.do_p)
-        return;
-    __syncthreads();
 
     // ---- phase 3: p_new on the tile, injection, m0 correlation -------------------------------------------
     const int ie0 = P.inj_it > 0 ? P.inj_off[tile] : 0, ie1 = P.inj_it > 0 ? P.inj_off[tile + 1] : 0;
@@ -250,13 +263,18 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
         if (gx >= ld || gy >= ny)
             continue;
         const long long q = (long long)gy * ld + gx;
+        Chunk<T> g0 = {}, pm1 = {};
+        if (ADJ) {
+            g0 = ldg_chunk(P.g0 + q);
+            pm1 = ldg_chunk(P.pc_itm1 + q);
+        }
         const Chunk<T> m0 = ldg_chunk(P.m0 + q);
-        const T *vxs = svx + r * SW + 4 * c + 8;
+        const T *vxs = svx + r * SW + 4 * c;
         const Chunk<T> xa = ldg_chunk(vxs - 4), xb = ldg_chunk(vxs), xc = ldg_chunk(vxs + 4);
         const T wx[7] = {xa.v[2], xa.v[3], xb.v[0], xb.v[1], xb.v[2], xb.v[3], xc.v[0]}; // vx at columns 4c-2 .. 4c+4
         const T *vys = svy + (r + 2) * TX + 4 * c;
         const Chunk<T> ya = ldg_chunk(vys - 2 * TX), yb = ldg_chunk(vys - TX), yc = ldg_chunk(vys), yd = ldg_chunk(vys + TX);
-        const Chunk<T> pin = ldg_chunk(sp + (r + 3) * SW + 4 * c + 8);
+        const Chunk<T> pin = ldg_chunk(sp + r * SW + 4 * c);
         Chunk<T> out = pin;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -289,9 +307,229 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
                 out.v[cell & 3] = out.v[cell & 3] + P.inj_tf[(size_t)P.inj_idx[e] * P.inj_nt + (P.inj_it - 1)];
         }
         if (ADJ) { // grad_m0 = grad_m0 - adjp * (p_it - p_itm1) * (1/dt), all in T (correlate_gradient_xPU.jl:12-21)
-            Chunk<T> g0 = ldg_chunk(P.g0 + q);
-            const Chunk<T> pit = ldg_chunk(spi + (r + 1) * SW + 4 * c + 8);
-            const Chunk<T> pm1 = ldg_chunk(P.pc_itm1 + q);
+            const Chunk<T> pit = ldg_chunk(spi + r * SW + 4 * c);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const T d = pit.v[e] - pm1.v[e];
+                const T t = out.v[e] * d;
+                g0.v[e] = g0.v[e] - t * P.inv_dt;
+            }
+            st_chunk(P.g0 + q, g0);
+        }
+        st_chunk(P.p_out + q, out);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interior tiles (no C-PML strip, no grid edge inside the tile or its halo): fixed thread -> cell mapping.
+// lane = 16-byte chunk column, warp w owns rows w, w+8, ... ; every loop below has a compile-time trip
+// count, so the index arithmetic of the generic body (divisions, range tests) disappears.
+// ------------------------------------------------------------------------------------------------
+template <class T, class CT>
+struct Fd4 {
+    // reference-faithful form: left-associated sum of weight * sample in CT, then * 1/spacing
+    static __device__ __forceinline__ CT d(const VdFusedParams<T> &P, T fm1, T f0, T f1, T f2, T inv) { return fd4<T, CT>(P, fm1, f0, f1, f2, inv); }
+    static __device__ __forceinline__ T upd(T a, T m, CT D) { return (T)((CT)a - (CT)m * D); }
+    static __device__ __forceinline__ T acc(T g, T a, CT D) { return (T)((CT)g + (CT)a * D); }
+};
+template <>
+struct Fd4<float, float> {
+    // SWB_FLAG_FAST_F32: (9/8 (f1 - f0) - 1/24 (f2 - fm1)) / spacing with fused multiply-adds
+    static __device__ __forceinline__ float d(const VdFusedParams<float> &, float fm1, float f0, float f1, float f2, float inv)
+    {
+        return __fmaf_rn(1.125f, f1 - f0, (-1.0f / 24.0f) * (f2 - fm1)) * inv;
+    }
+    static __device__ __forceinline__ float upd(float a, float m, float D) { return __fmaf_rn(-m, D, a); }
+    static __device__ __forceinline__ float acc(float g, float a, float D) { return __fmaf_rn(a, D, g); }
+};
+
+template <class T, class CT, bool ADJ, int TY>
+__device__ __forceinline__ void vd_tile_interior(const VdFusedParams<T> &P, unsigned char *smem_raw)
+{
+    typedef VdSmem<T, TY, ADJ> L;
+    typedef Fd4<T, CT> A;
+    constexpr int NW = NTHR / 32;
+    static_assert(NCH == 32, "one lane per chunk column");
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    T *sp = sm + L::P_OFF + 3 * SW + 8, *svx = sm + L::VX_OFF + 8, *sm1x = sm + L::M1X_OFF + 8;
+    T *svy = sm + L::VY_OFF, *sm1y = sm + L::M1Y_OFF, *spi = sm + L::PI_OFF + SW + 8;
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const long long ld = P.ld;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const long long o = (long long)y0 * ld + x0 + 4 * lane; // this lane's chunk in row 0 of the tile
+    // lanes 0..3 additionally fetch the halo chunks -2, -1, NCH, NCH+1 of a row
+    const int hc = lane < 2 ? lane - 2 - lane : NCH + (lane - 2) - lane; // chunk offset relative to this lane's own chunk
+
+    // ---- phase 1: everything the tile needs goes into shared memory with cp.async ----------------------
+#pragma unroll
+    for (int k = 0; k < (TY + 6 + NW - 1) / NW; ++k) { // p_in rows -3 .. TY+2
+        const int r = w + NW * k - 3;
+        if (r < TY + 3) {
+            cp_async_chunk(sp + r * SW + 4 * lane, P.p_in + o + (long long)r * ld);
+            if (lane < 4 && r >= 0 && r < TY)
+                cp_async_chunk(sp + r * SW + 4 * (lane + hc), P.p_in + o + (long long)r * ld + 4 * hc);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TY / NW; ++k) { // vx, m1x, m0 rows 0 .. TY-1 (vx / m1x with halo chunks -1 and NCH)
+        const int r = w + NW * k;
+        cp_async_chunk(svx + r * SW + 4 * lane, P.vx_in + o + (long long)r * ld);
+        if (P.do_v)
+            cp_async_chunk(sm1x + r * SW + 4 * lane, P.m1x + o + (long long)r * ld);
+        if (lane == 1 || lane == 2) {
+            cp_async_chunk(svx + r * SW + 4 * (lane + hc), P.vx_in + o + (long long)r * ld + 4 * hc);
+            if (P.do_v)
+                cp_async_chunk(sm1x + r * SW + 4 * (lane + hc), P.m1x + o + (long long)r * ld + 4 * hc);
+        }
+    }
+    Chunk<T> m0r[TY / NW]; // m0 is used once per cell: straight to registers, in flight together with the cp.async traffic
+    if (P.do_p) {
+#pragma unroll
+        for (int k = 0; k < TY / NW; ++k)
+            m0r[k] = ldg_chunk(P.m0 + o + (long long)(w + NW * k) * ld);
+    }
+#pragma unroll
+    for (int k = 0; k < (TY + 3 + NW - 1) / NW; ++k) { // vy, m1y rows -2 .. TY
+        const int rr = w + NW * k;
+        if (rr < TY + 3) {
+            cp_async_chunk(svy + rr * TX + 4 * lane, P.vy_in + o + (long long)(rr - 2) * ld);
+            if (P.do_v)
+                cp_async_chunk(sm1y + rr * TX + 4 * lane, P.m1y + o + (long long)(rr - 2) * ld);
+        }
+    }
+    if (ADJ) {
+#pragma unroll
+        for (int k = 0; k < (TY + 3 + NW - 1) / NW; ++k) { // p_it rows -1 .. TY+1, chunks -1 .. NCH
+            const int r = w + NW * k - 1;
+            if (r < TY + 2) {
+                cp_async_chunk(spi + r * SW + 4 * lane, P.pc_it + o + (long long)r * ld);
+                if (lane == 1 || lane == 2)
+                    cp_async_chunk(spi + r * SW + 4 * (lane + hc), P.pc_it + o + (long long)r * ld + 4 * hc);
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    if (P.rec_it > 0) { // record_receivers!
+        const int e0 = P.rec_off[tile], e1 = P.rec_off[tile + 1];
+        for (int e = e0 + (int)threadIdx.x; e < e1; e += NTHR) {
+            const int cell = P.rec_cell[e];
+            const int r = cell / TX, c = cell - r * TX;
+            P.traces[(size_t)P.rec_idx[e] * P.rec_nt + (P.rec_it - 1)] = sp[r * SW + c];
+        }
+    }
+
+    if (P.do_v) {
+        // ---- phase 2a: vx_new, own chunks ----------------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < TY / NW; ++k) {
+            const int r = w + NW * k;
+            T *vs = svx + r * SW + 4 * lane;
+            const Chunk<T> vin = ldg_chunk(vs), m1 = ldg_chunk(sm1x + r * SW + 4 * lane);
+            const T *ps = sp + r * SW + 4 * lane;
+            const Chunk<T> pa = ldg_chunk(ps - 4), pb = ldg_chunk(ps), pc = ldg_chunk(ps + 4);
+            const long long q = o + (long long)r * ld;
+            Chunk<T> out;
+            const CT D0 = A::d(P, pa.v[3], pb.v[0], pb.v[1], pb.v[2], P.inv_dx), D1 = A::d(P, pb.v[0], pb.v[1], pb.v[2], pb.v[3], P.inv_dx);
+            const CT D2 = A::d(P, pb.v[1], pb.v[2], pb.v[3], pc.v[0], P.inv_dx), D3 = A::d(P, pb.v[2], pb.v[3], pc.v[0], pc.v[1], P.inv_dx);
+            out.v[0] = A::upd(vin.v[0], m1.v[0], D0), out.v[1] = A::upd(vin.v[1], m1.v[1], D1);
+            out.v[2] = A::upd(vin.v[2], m1.v[2], D2), out.v[3] = A::upd(vin.v[3], m1.v[3], D3);
+            st_chunk(vs, out);
+            st_chunk(P.vx_out + q, out);
+            if (ADJ) {
+                Chunk<T> g1 = ldg_chunk(P.g1x + q);
+                const T *is = spi + r * SW + 4 * lane;
+                const Chunk<T> ia = ldg_chunk(is - 4), ib = ldg_chunk(is), ic = ldg_chunk(is + 4);
+                g1.v[0] = A::acc(g1.v[0], out.v[0], A::d(P, ia.v[3], ib.v[0], ib.v[1], ib.v[2], P.inv_dx));
+                g1.v[1] = A::acc(g1.v[1], out.v[1], A::d(P, ib.v[0], ib.v[1], ib.v[2], ib.v[3], P.inv_dx));
+                g1.v[2] = A::acc(g1.v[2], out.v[2], A::d(P, ib.v[1], ib.v[2], ib.v[3], ic.v[0], P.inv_dx));
+                g1.v[3] = A::acc(g1.v[3], out.v[3], A::d(P, ib.v[2], ib.v[3], ic.v[0], ic.v[1], P.inv_dx));
+                st_chunk(P.g1x + q, g1);
+            }
+        }
+        // halo columns -2, -1 and TX, TX+1 (recomputed, not stored): 2 columns x 2 sides x TY rows = 4 TY items
+        if (threadIdx.x < 4 * TY) {
+            const int r = threadIdx.x >> 2, j = threadIdx.x & 3;
+            const int col = j < 2 ? j - 2 : TX + (j - 2);
+            const T *ps = sp + r * SW + col;
+            const CT D = A::d(P, ps[-1], ps[0], ps[1], ps[2], P.inv_dx);
+            svx[r * SW + col] = A::upd(svx[r * SW + col], sm1x[r * SW + col], D);
+        }
+        // ---- phase 2b: vy_new on rows -2 .. TY -----------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < (TY + 3 + NW - 1) / NW; ++k) {
+            const int rr = w + NW * k;
+            if (rr < TY + 3) {
+                const int r = rr - 2;
+                T *vs = svy + rr * TX + 4 * lane;
+                const Chunk<T> vin = ldg_chunk(vs), m1 = ldg_chunk(sm1y + rr * TX + 4 * lane);
+                const T *ps = sp + r * SW + 4 * lane;
+                const Chunk<T> pa = ldg_chunk(ps - SW), pb = ldg_chunk(ps), pc = ldg_chunk(ps + SW), pd = ldg_chunk(ps + 2 * SW);
+                Chunk<T> out;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    out.v[e] = A::upd(vin.v[e], m1.v[e], A::d(P, pa.v[e], pb.v[e], pc.v[e], pd.v[e], P.inv_dy));
+                st_chunk(vs, out);
+                if (r >= 0 && r < TY) {
+                    const long long q = o + (long long)r * ld;
+                    st_chunk(P.vy_out + q, out);
+                    if (ADJ) {
+                        Chunk<T> g1 = ldg_chunk(P.g1y + q);
+                        const T *is = spi + r * SW + 4 * lane;
+                        const Chunk<T> ia = ldg_chunk(is - SW), ib = ldg_chunk(is), ic = ldg_chunk(is + SW), id = ldg_chunk(is + 2 * SW);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            g1.v[e] = A::acc(g1.v[e], out.v[e], A::d(P, ia.v[e], ib.v[e], ic.v[e], id.v[e], P.inv_dy));
+                        st_chunk(P.g1y + q, g1);
+                    }
+                }
+            }
+        }
+        if (!P.do_p)
+            return;
+        __syncthreads();
+    }
+
+    // ---- phase 3: p_new, injection, m0 correlation -------------------------------------------------------
+    const int ie0 = P.inj_it > 0 ? P.inj_off[tile] : 0, ie1 = P.inj_it > 0 ? P.inj_off[tile + 1] : 0;
+#pragma unroll
+    for (int k = 0; k < TY / NW; ++k) {
+        const int r = w + NW * k;
+        const long long q = o + (long long)r * ld;
+        Chunk<T> g0 = {}, pm1 = {};
+        if (ADJ) {
+            g0 = ldg_chunk(P.g0 + q);
+            pm1 = ldg_chunk(P.pc_itm1 + q);
+        }
+        const Chunk<T> m0 = m0r[k];
+        const T *vxs = svx + r * SW + 4 * lane;
+        const Chunk<T> xa = ldg_chunk(vxs - 4), xb = ldg_chunk(vxs), xc = ldg_chunk(vxs + 4);
+        const T *vys = svy + (r + 2) * TX + 4 * lane;
+        const Chunk<T> ya = ldg_chunk(vys - 2 * TX), yb = ldg_chunk(vys - TX), yc = ldg_chunk(vys), yd = ldg_chunk(vys + TX);
+        const Chunk<T> pin = ldg_chunk(sp + r * SW + 4 * lane);
+        CT Dx[4];
+        Dx[0] = A::d(P, xa.v[2], xa.v[3], xb.v[0], xb.v[1], P.inv_dx), Dx[1] = A::d(P, xa.v[3], xb.v[0], xb.v[1], xb.v[2], P.inv_dx);
+        Dx[2] = A::d(P, xb.v[0], xb.v[1], xb.v[2], xb.v[3], P.inv_dx), Dx[3] = A::d(P, xb.v[1], xb.v[2], xb.v[3], xc.v[0], P.inv_dx);
+        Chunk<T> out;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            out.v[e] = A::upd(pin.v[e], m0.v[e], Dx[e] + A::d(P, ya.v[e], yb.v[e], yc.v[e], yd.v[e], P.inv_dy));
+        for (int e = ie0; e < ie1; ++e) { // inject_sources!, this tile's entries in source-index order
+            const int cell = P.inj_cell[e];
+            if ((cell >> 2) == r * NCH + lane) {
+                const T add = P.inj_tf[(size_t)P.inj_idx[e] * P.inj_nt + (P.inj_it - 1)];
+                const int sub = cell & 3;
+                out.v[0] = sub == 0 ? out.v[0] + add : out.v[0];
+                out.v[1] = sub == 1 ? out.v[1] + add : out.v[1];
+                out.v[2] = sub == 2 ? out.v[2] + add : out.v[2];
+                out.v[3] = sub == 3 ? out.v[3] + add : out.v[3];
+            }
+        }
+        if (ADJ) {
+            const Chunk<T> pit = ldg_chunk(spi + r * SW + 4 * lane);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const T d = pit.v[e] - pm1.v[e];
@@ -305,7 +543,7 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
 }
 
 template <class T, class CT, bool ADJ, int TY>
-__global__ void __launch_bounds__(NTHR) vd_fused_kernel(const VdFusedParams<T> P)
+__global__ void __launch_bounds__(NTHR, sizeof(T) == 4 ? (ADJ ? 3 : 4) : 1) vd_fused_kernel(const VdFusedParams<T> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, h = P.halo;
@@ -314,13 +552,13 @@ __global__ void __launch_bounds__(NTHR) vd_fused_kernel(const VdFusedParams<T> P
     if (edge)
         vd_tile<T, CT, ADJ, TY, true>(P, smem_raw);
     else
-        vd_tile<T, CT, ADJ, TY, false>(P, smem_raw);
+        vd_tile_interior<T, CT, ADJ, TY>(P, smem_raw);
 }
 
 template <class T, class CT, bool ADJ, int TY>
 void launch_one(const VdFusedParams<T> &P, cudaStream_t st)
 {
-    const size_t smem = sizeof(T) * ((size_t)(TY + 6) * SW + (size_t)TY * SW + (size_t)(TY + 3) * TX + (ADJ ? (size_t)(TY + 3) * SW : 0));
+    const size_t smem = sizeof(T) * (size_t)VdSmem<T, TY, ADJ>::TOTAL;
     auto kern = vd_fused_kernel<T, CT, ADJ, TY>;
     static bool configured = false; // per instantiation
     if (!configured) {

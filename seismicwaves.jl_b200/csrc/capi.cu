@@ -304,6 +304,11 @@ int32_t swb_sim_kernel_timing(swb_sim *sim, int32_t enable, double *ms_total, in
     SIM_CALL(sim->impl->kernel_timing(enable, ms_total, launches))
 }
 
+int32_t swb_sim_kernel_timing_class(swb_sim *sim, int32_t cls, double *ms_total, int64_t *launches)
+{
+    SIM_CALL(sim->impl->kernel_timing_class(cls, ms_total, launches))
+}
+
 // ---- 4. multi-GPU (NCCL resolved at run time so that the library loads on hosts without it) ----------
 struct swb_comm {
     ncclComm_t comm = nullptr;

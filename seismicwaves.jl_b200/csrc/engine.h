@@ -124,6 +124,7 @@ class SimBase {
     void get_total_gradient(int which, void *host_out);
     void get_snapshot(int64_t it, int field, void *host_out);
     void kernel_timing(int enable, double *ms_total, int64_t *launches);
+    void kernel_timing_class(int cls, double *ms_total, int64_t *launches);
     int64_t device_bytes() const { return dev_bytes_; }
 
   protected:
@@ -135,7 +136,7 @@ class SimBase {
     void sync() { SWB_CUDA(cudaStreamSynchronize(stream)); }
     swb_cpml_axis cpml_axis(int ax) const;
     // timing of the dominant (stencil) kernel
-    void tic();
+    void tic(int cls = 0); // cls 0: forward / re-forward step, 1: adjoint step (+ correlation)
     void toc();
 
     DevBuf cpml_[3][4]; // a, a_h, b, b_h per axis
@@ -151,9 +152,13 @@ class SimBase {
     int64_t dev_bytes_ = 0;
     bool timing_ = false, tsampled_ = false;
     int64_t tcount_ = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev_;
-    double t_ms_ = 0;
-    int64_t t_n_ = 0;
+    struct TimedLaunch {
+        cudaEvent_t a, b;
+        int cls;
+    };
+    std::vector<TimedLaunch> tev_;
+    double t_ms_[2] = {0, 0};
+    int64_t t_n_[2] = {0, 0};
 };
 
 SimBase *make_acoustic_cd(const swb_sim_desc &d);

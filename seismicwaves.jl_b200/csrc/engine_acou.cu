@@ -282,7 +282,7 @@ class AcousticCD : public SimBase {
         a.src.tf = adjsrc_.p;
         a.src.nt = desc.nt;
         a.it = it;
-        tic();
+        tic(1);
         cd_step(a, false);
         toc();
         acur_[0] = acur_[1];
@@ -606,7 +606,7 @@ class AcousticVD : public SimBase {
         a.src.tf = adjsrc_.p;
         a.src.nt = desc.nt;
         a.it = it;
-        tic();
+        tic(1);
         vd_step(a, true);
         toc();
         cell_updates += (int64_t)ncells();

@@ -259,8 +259,8 @@ SimBase::~SimBase()
         cudaStreamDestroy(stream);
     }
     for (auto &e : tev_) {
-        cudaEventDestroy(e.first);
-        cudaEventDestroy(e.second);
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
     }
 }
 
@@ -383,24 +383,25 @@ void SimBase::get_snapshot(int64_t it, int field, void *host_out)
     std::memcpy(host_out, s->second[field].data(), s->second[field].size());
 }
 
-void SimBase::tic()
+void SimBase::tic(int cls)
 {
     tsampled_ = false;
     if (!timing_ || (tcount_++ % 8) != 0) // sample every 8th step: keeps the event overhead out of the timed region
         return;
     tsampled_ = true;
-    cudaEvent_t a, b;
-    SWB_CUDA(cudaEventCreate(&a));
-    SWB_CUDA(cudaEventCreate(&b));
-    SWB_CUDA(cudaEventRecord(a, stream));
-    tev_.push_back({a, b});
+    TimedLaunch t;
+    t.cls = cls ? 1 : 0;
+    SWB_CUDA(cudaEventCreate(&t.a));
+    SWB_CUDA(cudaEventCreate(&t.b));
+    SWB_CUDA(cudaEventRecord(t.a, stream));
+    tev_.push_back(t);
 }
 
 void SimBase::toc()
 {
     if (!timing_ || !tsampled_ || tev_.empty())
         return;
-    SWB_CUDA(cudaEventRecord(tev_.back().second, stream));
+    SWB_CUDA(cudaEventRecord(tev_.back().b, stream));
 }
 
 void SimBase::kernel_timing(int enable, double *ms_total, int64_t *launches)
@@ -409,25 +410,35 @@ void SimBase::kernel_timing(int enable, double *ms_total, int64_t *launches)
     SWB_CUDA(cudaStreamSynchronize(stream));
     for (auto &e : tev_) {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) {
-            t_ms_ += ms;
-            t_n_ += 1;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+            t_ms_[e.cls] += ms;
+            t_n_[e.cls] += 1;
         }
-        cudaEventDestroy(e.first);
-        cudaEventDestroy(e.second);
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
     }
     tev_.clear();
     if (ms_total)
-        *ms_total = t_ms_;
+        *ms_total = t_ms_[0] + t_ms_[1];
     if (launches)
-        *launches = t_n_;
+        *launches = t_n_[0] + t_n_[1];
     if (enable == 0 || enable == 1) {
-        if ((enable == 1) != timing_) {
-            t_ms_ = 0;
-            t_n_ = 0;
+        if (enable == 1 && !timing_) {
+            t_ms_[0] = t_ms_[1] = 0;
+            t_n_[0] = t_n_[1] = 0;
         }
         timing_ = enable == 1;
     }
+}
+
+void SimBase::kernel_timing_class(int cls, double *ms_total, int64_t *launches)
+{
+    kernel_timing(-1, nullptr, nullptr);
+    SWB_REQUIRE(cls == 0 || cls == 1, "timing class must be 0 (forward) or 1 (adjoint)");
+    if (ms_total)
+        *ms_total = t_ms_[cls];
+    if (launches)
+        *launches = t_n_[cls];
 }
 
 } // namespace swb
