@@ -255,10 +255,10 @@ class _AcousticBase(WaveSimulation):
 
     def init_shot(self, shot) -> None:
         """init_shot! (shots/shot.jl:46-51): check_shot + init_bdc!."""
-        self.check_numerics(shot, float(np.min(self.matprop.vp)))
+        self.check_numerics(shot, self._vp_min)
         self.check_positions(shot.srcs.positions)
         self.check_positions(shot.recs.positions)
-        self._set_cpml(self.T(np.max(self.matprop.vp)), shot.srcs.domfreq)
+        self._set_cpml(self._vp_max, shot.srcs.domfreq)
 
     def _bind_scalar(self, shot, scal_srctf, possrcs, posrecs) -> None:
         self._possrcs, self._posrecs, self._srctf = possrcs, posrecs, scal_srctf
@@ -281,6 +281,7 @@ class AcousticCDCPMLWaveSimulation(_AcousticBase):
         assert np.all(vp > 0), "Pressure velocity material property must be positive!"
         self.check_courant_condition(vp)
         self.matprop = VpAcousticCDMaterialProperties(vp.copy(order="F"))
+        self._vp_min, self._vp_max = float(np.min(vp)), self.T(np.max(vp))  # reductions over the model once per update, not per shot
         arr = (C.c_void_p * 1)(self.matprop.vp.ctypes.data)
         _lib.check(self.lib.swb_sim_set_material(self._h, 1, arr, 0))
 
@@ -312,6 +313,7 @@ class AcousticVDStaggeredCPMLWaveSimulation(_AcousticBase):
         assert np.all(rho > 0), "Density material property must be positive!"
         self.check_courant_condition(vp)
         self.matprop = VpRhoAcousticVDMaterialProperties(vp.copy(order="F"), rho.copy(order="F"), interp_method=matprop.interp_method)
+        self._vp_min, self._vp_max = float(np.min(vp)), self.T(np.max(vp))
         arr = (C.c_void_p * 2)(self.matprop.vp.ctypes.data, self.matprop.rho.ctypes.data)
         _lib.check(self.lib.swb_sim_set_material(self._h, 2, arr, 0 if matprop.interp_method == "arithmetic" else 1))
 

@@ -129,6 +129,19 @@ class SimBase {
 
   protected:
     DevBuf dalloc(size_t bytes);
+    // (re)allocate only when the size changes, so that device pointers -- and with them captured CUDA graphs -- survive
+    // a re-bind with the same geometry; returns true if the pointer changed
+    bool ensure(DevBuf &b, size_t bytes);
+    virtual void pointers_changed() {}
+    // CUDA-graph replay of a fixed launch sequence: the first call captures `enqueue` on the sim's stream, later calls
+    // replay it (SWB_FLAG_NO_GRAPH: always enqueue eagerly).  `updates` = cell-updates the sequence performs.
+    struct Graph {
+        cudaGraphExec_t exec = nullptr;
+        int64_t updates = 0, launches = 0;
+    };
+    template <class F>
+    void run_graph(Graph &g, F &&enqueue);
+    void drop_graph(Graph &g);
     void upload(void *dst, const void *src, size_t bytes);
     void download(void *dst, const void *src, size_t bytes);
     void d2d(void *dst, const void *src, size_t bytes);
@@ -136,7 +149,9 @@ class SimBase {
     void sync() { SWB_CUDA(cudaStreamSynchronize(stream)); }
     swb_cpml_axis cpml_axis(int ax) const;
     // timing of the dominant (stencil) kernel
-    void tic(int cls = 0); // cls 0: forward / re-forward step, 1: adjoint step (+ correlation)
+    void tic(int cls = 0); // cls 0: forward / re-forward step, 1: adjoint step (+ correlation); samples every 8th call
+    // time a whole replayed sequence: n launches of class cls (+ n_aux re-forward launches inside an adjoint sequence)
+    void tic_group(int cls, int64_t n, int64_t n_aux = 0);
     void toc();
 
     DevBuf cpml_[3][4]; // a, a_h, b, b_h per axis
@@ -155,11 +170,53 @@ class SimBase {
     struct TimedLaunch {
         cudaEvent_t a, b;
         int cls;
+        int64_t n, n_aux;
     };
     std::vector<TimedLaunch> tev_;
-    double t_ms_[2] = {0, 0};
-    int64_t t_n_[2] = {0, 0};
+    double t_ms_[3] = {0, 0, 0};
+    int64_t t_n_[3] = {0, 0, 0};
+    bool capturing_ = false;
 };
+
+template <class F>
+void SimBase::run_graph(Graph &g, F &&enqueue)
+{
+    if (desc.flags & SWB_FLAG_NO_GRAPH) {
+        enqueue();
+        return;
+    }
+    if (!g.exec) {
+        const int64_t cu0 = cell_updates;
+        const long long l0 = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        SWB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+        capturing_ = true;
+        try {
+            enqueue();
+            capturing_ = false;
+        } catch (...) {
+            capturing_ = false;
+            cudaStreamEndCapture(stream, &graph);
+            if (graph)
+                cudaGraphDestroy(graph);
+            throw;
+        }
+        SWB_CUDA(cudaStreamEndCapture(stream, &graph));
+        g.updates = cell_updates - cu0;
+        g.launches = g_launches.load() - l0;
+        cell_updates = cu0; // counted per replay below
+        g_launches.fetch_sub(g.launches);
+        cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            g.exec = nullptr;
+            throw Error(SWB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        }
+    }
+    SWB_CUDA(cudaGraphLaunch(g.exec, stream));
+    cell_updates += g.updates;
+    g_launches.fetch_add(g.launches);
+}
 
 SimBase *make_acoustic_cd(const swb_sim_desc &d);
 SimBase *make_acoustic_vd(const swb_sim_desc &d);

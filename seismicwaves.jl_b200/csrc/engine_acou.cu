@@ -102,7 +102,7 @@ class AcousticCD : public SimBase {
         const size_t ntr = (size_t)desc.nt * nrec_;
         void *obs = nullptr;
         if (host_obs) { // observed data staged in the (not yet used) adjoint-source buffer's twin
-            obs_ = dalloc(adjsrc_.bytes);
+            ensure(obs_, adjsrc_.bytes);
             upload(obs_.p, host_obs, obs_.bytes);
             obs = obs_.p;
         }
@@ -178,9 +178,11 @@ class AcousticCD : public SimBase {
     {
         if (radius == 0 || npos == 0)
             return;
-        DevBuf dp = dalloc(esize * npos * desc.ndim);
-        upload(dp.p, hostpos, dp.bytes);
-        post_mute(desc.dtype, desc.ndim, desc.n, desc.spacing, arr, npos, dp.p, radius, stream);
+        // persistent scratch: cudaMalloc / cudaFree inside the shot loop serialise the device (and were measured at
+        // up to a second per call next to instantiated graphs)
+        ensure(mute_pos_, esize * npos * desc.ndim);
+        upload(mute_pos_.p, hostpos, mute_pos_.bytes);
+        post_mute(desc.dtype, desc.ndim, desc.n, desc.spacing, arr, npos, mute_pos_.p, radius, stream);
         sync();
     }
 
@@ -330,7 +332,7 @@ class AcousticCD : public SimBase {
     }
 
     DevBuf fact_, vp_, p_[3], psi_[3], xi_[3];
-    DevBuf grad_, work_, adj_[3], psi_adj_[3], xi_adj_[3], misfit_acc_, obs_;
+    DevBuf grad_, work_, adj_[3], psi_adj_[3], xi_adj_[3], misfit_acc_, obs_, mute_pos_;
     void *cur_[3] = {nullptr, nullptr, nullptr};
     void *acur_[3] = {nullptr, nullptr, nullptr};
     std::unique_ptr<DeviceCheckpointer> ckpt_;
@@ -452,7 +454,7 @@ class AcousticVD : public SimBase {
         gradient_forward(host_seis);
         void *obs = nullptr;
         if (host_obs) {
-            obs_ = dalloc(adjsrc_.bytes);
+            ensure(obs_, adjsrc_.bytes);
             upload(obs_.p, host_obs, obs_.bytes);
             obs = obs_.p;
         }
@@ -478,15 +480,15 @@ class AcousticVD : public SimBase {
         // acou_gradient.jl:177-202
         d2d(work_.p, g0_.p, g0_.bytes);
         post_vd_backinterp(desc.dtype, desc.n, rho_.p, interp_, g1s_[0].p, g1s_[1].p, g1_.p, stream);
-        DevBuf sp, rp;
+        DevBuf &sp = mute_pos_[0], &rp = mute_pos_[1]; // persistent scratch (no cudaMalloc / cudaFree inside the shot loop)
         if (rs != 0 && nsrcpos > 0) {
-            sp = dalloc(esize * nsrcpos * 2);
+            ensure(sp, esize * nsrcpos * 2);
             upload(sp.p, srcpos, sp.bytes);
             post_mute(desc.dtype, 2, desc.n, desc.spacing, work_.p, nsrcpos, sp.p, rs, stream);
             post_mute(desc.dtype, 2, desc.n, desc.spacing, g1_.p, nsrcpos, sp.p, rs, stream);
         }
         if (rr != 0 && nrecpos > 0) {
-            rp = dalloc(esize * nrecpos * 2);
+            ensure(rp, esize * nrecpos * 2);
             upload(rp.p, recpos, rp.bytes);
             post_mute(desc.dtype, 2, desc.n, desc.spacing, work_.p, nrecpos, rp.p, rr, stream);
             post_mute(desc.dtype, 2, desc.n, desc.spacing, g1_.p, nrecpos, rp.p, rr, stream);
@@ -665,7 +667,7 @@ class AcousticVD : public SimBase {
     int64_t nx_, ny_;
     int interp_ = 0;
     DevBuf vp_, rho_, m0_, m1_[2], p_, v_[2], psi_[2], xi_[2];
-    DevBuf g0_, g1s_[2], g1_, work_, ap_, av_[2], psi_adj_[2], xi_adj_[2], misfit_acc_, obs_;
+    DevBuf g0_, g1s_[2], g1_, work_, ap_, av_[2], psi_adj_[2], xi_adj_[2], misfit_acc_, obs_, mute_pos_[2];
     std::unique_ptr<DeviceCheckpointer> ckpt_;
     bool mat_set_ = false;
 };

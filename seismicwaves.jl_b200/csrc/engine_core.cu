@@ -272,6 +272,24 @@ DevBuf SimBase::dalloc(size_t bytes)
     return b;
 }
 
+bool SimBase::ensure(DevBuf &b, size_t bytes)
+{
+    if (b.p != nullptr && b.bytes == bytes)
+        return false;
+    dev_bytes_ -= (int64_t)b.bytes;
+    b = dalloc(bytes);
+    return true;
+}
+
+void SimBase::drop_graph(Graph &g)
+{
+    if (g.exec) {
+        cudaStreamSynchronize(stream);
+        cudaGraphExecDestroy(g.exec);
+    }
+    g = Graph();
+}
+
 void SimBase::upload(void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0)
@@ -336,12 +354,14 @@ void SimBase::bind_scalar_shot(int64_t nsrc, const int64_t *possrcs, const void 
             SWB_REQUIRE(posrecs[r + d * nrec] >= 1 && posrecs[r + d * nrec] <= desc.n[d], "receiver position outside the grid");
     nsrc_ = nsrc;
     nrec_ = nrec;
-    possrc_ = dalloc(sizeof(int64_t) * nsrc * desc.ndim);
-    posrec_ = dalloc(sizeof(int64_t) * nrec * desc.ndim);
-    srctf_ = dalloc(esize * desc.nt * nsrc);
-    traces_ = dalloc(esize * desc.nt * nrec);
+    bool ch = ensure(possrc_, sizeof(int64_t) * nsrc * desc.ndim);
+    ch |= ensure(posrec_, sizeof(int64_t) * nrec * desc.ndim);
+    ch |= ensure(srctf_, esize * desc.nt * nsrc);
+    ch |= ensure(traces_, esize * desc.nt * nrec);
     if (desc.gradient)
-        adjsrc_ = dalloc(esize * desc.nt * nrec);
+        ch |= ensure(adjsrc_, esize * desc.nt * nrec);
+    if (ch)
+        pointers_changed();
     upload(possrc_.p, possrcs, possrc_.bytes);
     upload(posrec_.p, posrecs, posrec_.bytes);
     upload(srctf_.p, srctf, srctf_.bytes);
@@ -386,11 +406,29 @@ void SimBase::get_snapshot(int64_t it, int field, void *host_out)
 void SimBase::tic(int cls)
 {
     tsampled_ = false;
-    if (!timing_ || (tcount_++ % 8) != 0) // sample every 8th step: keeps the event overhead out of the timed region
+    if (!timing_ || capturing_ || (tcount_++ % 8) != 0) // sample every 8th step: keeps the event overhead out of the timed region
         return;
     tsampled_ = true;
     TimedLaunch t;
     t.cls = cls ? 1 : 0;
+    t.n = 1;
+    t.n_aux = 0;
+    SWB_CUDA(cudaEventCreate(&t.a));
+    SWB_CUDA(cudaEventCreate(&t.b));
+    SWB_CUDA(cudaEventRecord(t.a, stream));
+    tev_.push_back(t);
+}
+
+void SimBase::tic_group(int cls, int64_t n, int64_t n_aux)
+{
+    tsampled_ = false;
+    if (!timing_ || capturing_)
+        return;
+    tsampled_ = true;
+    TimedLaunch t;
+    t.cls = cls ? 1 : 0;
+    t.n = n;
+    t.n_aux = n_aux;
     SWB_CUDA(cudaEventCreate(&t.a));
     SWB_CUDA(cudaEventCreate(&t.b));
     SWB_CUDA(cudaEventRecord(t.a, stream));
@@ -402,6 +440,7 @@ void SimBase::toc()
     if (!timing_ || !tsampled_ || tev_.empty())
         return;
     SWB_CUDA(cudaEventRecord(tev_.back().b, stream));
+    tsampled_ = false;
 }
 
 void SimBase::kernel_timing(int enable, double *ms_total, int64_t *launches)
@@ -412,7 +451,8 @@ void SimBase::kernel_timing(int enable, double *ms_total, int64_t *launches)
         float ms = 0;
         if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
             t_ms_[e.cls] += ms;
-            t_n_[e.cls] += 1;
+            t_n_[e.cls] += e.n;
+            t_n_[2] += e.n_aux;
         }
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
@@ -424,8 +464,8 @@ void SimBase::kernel_timing(int enable, double *ms_total, int64_t *launches)
         *launches = t_n_[0] + t_n_[1];
     if (enable == 0 || enable == 1) {
         if (enable == 1 && !timing_) {
-            t_ms_[0] = t_ms_[1] = 0;
-            t_n_[0] = t_n_[1] = 0;
+            t_ms_[0] = t_ms_[1] = t_ms_[2] = 0;
+            t_n_[0] = t_n_[1] = t_n_[2] = 0;
         }
         timing_ = enable == 1;
     }
@@ -434,7 +474,7 @@ void SimBase::kernel_timing(int enable, double *ms_total, int64_t *launches)
 void SimBase::kernel_timing_class(int cls, double *ms_total, int64_t *launches)
 {
     kernel_timing(-1, nullptr, nullptr);
-    SWB_REQUIRE(cls == 0 || cls == 1, "timing class must be 0 (forward) or 1 (adjoint)");
+    SWB_REQUIRE(cls >= 0 && cls <= 2, "timing class must be 0 (forward), 1 (adjoint) or 2 (re-forward launches inside class-1 time)");
     if (ms_total)
         *ms_total = t_ms_[cls];
     if (launches)
