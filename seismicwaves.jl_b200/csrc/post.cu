@@ -3,6 +3,10 @@
 // L2 adjoint source + misfit, gradient accumulation.  Each kernel reproduces the reference's
 // arithmetic (types and association order) so that results match the CPU path.
 #include "common.cuh"
+#include <map>
+#include <mutex>
+#include <vector>
+#include <algorithm>
 #include "kernels.h"
 #include <vector>
 #include <algorithm>
@@ -125,6 +129,28 @@ __global__ void mute_kernel(T *arr, int ndim, long long n0, long long n1, long l
     }
 }
 
+// grow-only per-device scratch for the window centres: a stream-ordered cudaMallocAsync / cudaFreeAsync pair here made
+// the memory pool trim itself at the following synchronisation, which was measured at 0.1 - 1 s per shot
+static void *mute_scratch(size_t bytes)
+{
+    static std::mutex mtx;
+    static std::map<int, std::pair<void *, size_t>> cache;
+    std::lock_guard<std::mutex> lk(mtx);
+    int dev = 0;
+    SWB_CUDA(cudaGetDevice(&dev));
+    auto &e = cache[dev];
+    if (e.second < bytes) {
+        if (e.first)
+            cudaFree(e.first);
+        e.first = nullptr;
+        e.second = 0;
+        const size_t want = std::max<size_t>(bytes, 1 << 16);
+        SWB_CUDA(cudaMalloc(&e.first, want));
+        e.second = want;
+    }
+    return e.first;
+}
+
 template <class T>
 static void mute_impl(int ndim, const int64_t *n, const double *spacing, void *arr, int64_t npos, const void *dev_positions, int radius, cudaStream_t st)
 {
@@ -161,8 +187,7 @@ static void mute_impl(int ndim, const int64_t *n, const double *spacing, void *a
         if (hi[d] < lo[d])
             return;
     }
-    long long *dwin = nullptr;
-    SWB_CUDA(cudaMallocAsync((void **)&dwin, win.size() * sizeof(long long), st));
+    long long *dwin = (long long *)mute_scratch(win.size() * sizeof(long long));
     SWB_CUDA(cudaMemcpyAsync(dwin, win.data(), win.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
     const long long e0 = hi[0] - lo[0] + 1, e1 = ndim >= 2 ? hi[1] - lo[1] + 1 : 1, e2 = ndim >= 3 ? hi[2] - lo[2] + 1 : 1;
     mute_kernel<T><<<grid1d((size_t)e0 * e1 * e2), 256, 0, st>>>((T *)arr, ndim, n[0], ndim >= 2 ? n[1] : 1, ndim >= 3 ? n[2] : 1, (T)spacing[0],
@@ -171,7 +196,6 @@ static void mute_impl(int ndim, const int64_t *n, const double *spacing, void *a
     check_launch("mute");
     count_launch();
     SWB_CUDA(cudaStreamSynchronize(st)); // `win` (host) was the async copy source
-    SWB_CUDA(cudaFreeAsync(dwin, st));
 }
 
 void post_mute(int dtype, int ndim, const int64_t *n, const double *spacing, void *arr, int64_t npos, const void *dev_positions, int radius, cudaStream_t st)
