@@ -41,8 +41,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 def build(force: bool = False) -> None:
     """Compile oracle/libswref.so and libswref_omp.so with the committed Makefile."""
-    if force or not (os.path.exists(os.path.join(_HERE, "libswref.so")) and os.path.exists(os.path.join(_HERE, "libswref_omp.so"))):
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    # always defer to make: it rebuilds only when a source is newer than the libraries
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
 
 
 _LIBS: Dict[bool, C.CDLL] = {}
