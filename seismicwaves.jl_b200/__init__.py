@@ -7,6 +7,7 @@ from . import _lib, hostprep  # noqa: F401
 from ._lib import SwbError, device_count  # noqa: F401
 from .api import (AcousticCDCPMLWaveSimulation, AcousticVDStaggeredCPMLWaveSimulation, WaveSimulation, build_wavesim, swforward, swgradient,  # noqa: F401
                   swmisfit)
+from .elastic import ElasticIsoCPMLWaveSimulation  # noqa: F401
 from .hostprep import distribsrcs, gaussderivstf, gaussstf, rickerstf  # noqa: F401
 from .types import (CPMLBoundaryConditionParameters, ElasticIsoMaterialProperties, ExternalForceShot, ExternalForceSources, GradParameters,  # noqa: F401
                     InputParametersAcoustic, InputParametersElastic, L2Misfit, MomentTensor2D, MomentTensorShot, MomentTensorSources, RunParameters,

@@ -334,7 +334,7 @@ class AcousticVDStaggeredCPMLWaveSimulation(_AcousticBase):
 # ---------------------------------------------------------------------------------------------------------
 
 
-def build_wavesim(params, matprop, runparams: Optional[RunParameters] = None, gradparams: Optional[GradParameters] = None, gradient: bool = False):
+def build_wavesim(params, matprop, runparams: Optional[RunParameters] = None, gradparams: Optional[GradParameters] = None, gradient: bool = False, **kw):
     """build_wavesim (src/apis/build.jl:18-88)."""
     runparams = runparams or RunParameters()
     if gradparams is None and gradient:
@@ -352,7 +352,7 @@ def build_wavesim(params, matprop, runparams: Optional[RunParameters] = None, gr
         cls = ElasticIsoCPMLWaveSimulation
     else:
         raise TypeError(f"no WaveSimulation for ({type(params).__name__}, {type(matprop).__name__})")
-    return cls(params, matprop, bc, runparams, gradparams, gradient=gradient)
+    return cls(params, matprop, bc, runparams, gradparams, gradient=gradient, **kw)  # kw: sincinterp (elastic, ela_models.jl:208)
 
 
 def _run_swforward(wavesim: WaveSimulation, matprop, shots):

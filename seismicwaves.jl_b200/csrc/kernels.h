@@ -29,6 +29,9 @@ void post_mute(int dtype, int ndim, const int64_t *n, const double *spacing, voi
 void post_cd_chain_accumulate(int dtype, size_t n, const void *grad_raw_muted, const void *vp, void *total, cudaStream_t st);
 void post_vd_backinterp(int dtype, const int64_t *n, const void *rho, int interp, const void *g1x, const void *g1y, void *g1, cudaStream_t st);
 void post_vd_chain_accumulate(int dtype, size_t n, const void *g0, const void *g1, const void *vp, const void *rho, void *tot_vp, void *tot_rho, cudaStream_t st);
+void post_ela_props(int dtype, const int64_t *n, const void *rho, const void *mu, int interp_rho, int interp_mu, void *rho_ih, void *rho_jh, void *mu_hh, cudaStream_t st);
+void post_ela_backinterp(int dtype, const int64_t *n, const void *rho, const void *mu, int interp_rho, int interp_mu, const void *g_ri, const void *g_rj,
+                         const void *g_mh, const void *g_mu, void *out_rho, void *out_mu, cudaStream_t st);
 void post_l2_adjsrc(int dtype, size_t n, const void *syn, const void *obs_or_null, void *adjsrc, double *misfit_accum, cudaStream_t st);
 void post_axpy(int dtype, size_t n, const void *x, void *y, cudaStream_t st); // y += x
 

@@ -311,6 +311,116 @@ void post_vd_chain_accumulate(int dtype, size_t n, const void *g0, const void *g
     count_launch();
 }
 
+// ---- elastic: staggered material averages (precomp_elaprop!, ela_models.jl:156-173; utils/interpolations.jl:35-43) ----
+//   ρ_ihalf = interp(ρ, 1), ρ_jhalf = interp(ρ, 2), μ_ihalf_jhalf = interp(μ, [1, 2]); BSpline(Linear()) at half indices
+//   = nested two-point means with Float64 weights 0.5 (first axis innermost); harmonic = 1 ./ itp(1 ./ m)
+template <class T>
+__device__ __forceinline__ double mean2(T a, T b, int interp)
+{
+    if (interp == 0)
+        return 0.5 * (double)a + 0.5 * (double)b;
+    return 0.5 * (double)((T)1 / a) + 0.5 * (double)((T)1 / b); // caller inverts
+}
+template <class T>
+__global__ void ela_props_kernel(const T *rho, const T *mu, int irho, int imu, T *rho_ih, T *rho_jh, T *mu_hh, long long nx, long long nz)
+{
+    const size_t n = (size_t)nx * nz;
+    GRID_STRIDE(q, n)
+    {
+        const long long i = q % nx, j = q / nx;
+        if (i < nx - 1) {
+            const double m = mean2<T>(rho[q], rho[q + 1], irho);
+            rho_ih[(size_t)j * (nx - 1) + i] = (T)(irho == 0 ? m : 1.0 / m);
+        }
+        if (j < nz - 1) {
+            const double m = mean2<T>(rho[q], rho[q + nx], irho);
+            rho_jh[q] = (T)(irho == 0 ? m : 1.0 / m);
+        }
+        if (i < nx - 1 && j < nz - 1) {
+            const double a0 = mean2<T>(mu[q], mu[q + 1], imu), a1 = mean2<T>(mu[q + nx], mu[q + nx + 1], imu);
+            const double m = 0.5 * a0 + 0.5 * a1;
+            mu_hh[(size_t)j * (nx - 1) + i] = (T)(imu == 0 ? m : 1.0 / m);
+        }
+    }
+}
+
+void post_ela_props(int dtype, const int64_t *n, const void *rho, const void *mu, int interp_rho, int interp_mu, void *rho_ih, void *rho_jh, void *mu_hh,
+                    cudaStream_t st)
+{
+    const size_t nn = (size_t)n[0] * n[1];
+    if (dtype == SWB_F64)
+        ela_props_kernel<double><<<grid1d(nn), 256, 0, st>>>((const double *)rho, (const double *)mu, interp_rho, interp_mu, (double *)rho_ih, (double *)rho_jh,
+                                                            (double *)mu_hh, n[0], n[1]);
+    else
+        ela_props_kernel<float><<<grid1d(nn), 256, 0, st>>>((const float *)rho, (const float *)mu, interp_rho, interp_mu, (float *)rho_ih, (float *)rho_jh,
+                                                           (float *)mu_hh, n[0], n[1]);
+    check_launch("ela_props");
+    count_launch();
+}
+
+// ---- elastic: back_interp of the staggered gradients (ela_gradient.jl:163-165, utils/interpolations.jl:14-28,45-47) ----
+//   gradient_ρ = 0 + (back_interp(g_ρ_ihalf, 1) + back_interp(g_ρ_jhalf, 2));  gradient_μ = grad_μ + back_interp(g_μ_ihalf_jhalf, [1, 2])
+// 2-D back_interp visits the permutations (0,0), (0,1), (1,0), (1,1) in that order: cell (I,J) receives
+// g[I,J], g[I,J-1], g[I-1,J], g[I-1,J-1] (0-based staggered indices), each times ∂f∂m.
+template <class T>
+__device__ __forceinline__ double harm4_itp(const T *mu, long long nx, long long i, long long j)
+{ // harmonic interpolant at staggered point (i, j): 1 / (nested means of 1/μ)
+    const size_t q = (size_t)j * nx + i;
+    const double a0 = 0.5 * (double)((T)1 / mu[q]) + 0.5 * (double)((T)1 / mu[q + 1]);
+    const double a1 = 0.5 * (double)((T)1 / mu[q + nx]) + 0.5 * (double)((T)1 / mu[q + nx + 1]);
+    return 1.0 / (0.5 * a0 + 0.5 * a1);
+}
+template <class T>
+__global__ void ela_backinterp_kernel(const T *rho, const T *mu, int irho, int imu, const T *g_ri, const T *g_rj, const T *g_mh, const T *g_mu, T *out_rho,
+                                      T *out_mu, long long nx, long long nz)
+{
+    const size_t n = (size_t)nx * nz;
+    GRID_STRIDE(q, n)
+    {
+        const long long i = q % nx, j = q / nx;
+        const T m = rho[q];
+        const T mxn = i < nx - 1 ? rho[q + 1] : (T)0, mxp = i > 0 ? rho[q - 1] : (T)0;
+        const T mzn = j < nz - 1 ? rho[q + nx] : (T)0, mzp = j > 0 ? rho[q - nx] : (T)0;
+        const T bx = backinterp_pair<T>(i < nx - 1 ? g_ri[(size_t)j * (nx - 1) + i] : (T)0, i < nx - 1, i > 0 ? g_ri[(size_t)j * (nx - 1) + i - 1] : (T)0, i > 0,
+                                        irho, m, mxn, mxp);
+        const T bz = backinterp_pair<T>(j < nz - 1 ? g_rj[q] : (T)0, j < nz - 1, j > 0 ? g_rj[q - nx] : (T)0, j > 0, irho, m, mzn, mzp);
+        out_rho[q] = (T)0 + (bx + bz);
+        T res = (T)0;
+        const long long di[4] = {0, 0, -1, -1}, dj[4] = {0, -1, 0, -1};
+        const T mm = mu[q];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long si = i + di[k], sj = j + dj[k];
+            if (si < 0 || sj < 0 || si > nx - 2 || sj > nz - 2)
+                continue;
+            const T g = g_mh[(size_t)sj * (nx - 1) + si];
+            if (imu == 0)
+                res = res + g * (T)0.25;
+            else {
+                const double itp = harm4_itp<T>(mu, nx, si, sj);
+                const double w = ((itp * itp) / (double)(mm * mm)) / 4.0;
+                res = (T)((double)res + (double)g * w);
+            }
+        }
+        out_mu[q] = g_mu[q] + res;
+    }
+}
+
+void post_ela_backinterp(int dtype, const int64_t *n, const void *rho, const void *mu, int interp_rho, int interp_mu, const void *g_ri, const void *g_rj,
+                         const void *g_mh, const void *g_mu, void *out_rho, void *out_mu, cudaStream_t st)
+{
+    const size_t nn = (size_t)n[0] * n[1];
+    if (dtype == SWB_F64)
+        ela_backinterp_kernel<double><<<grid1d(nn), 256, 0, st>>>((const double *)rho, (const double *)mu, interp_rho, interp_mu, (const double *)g_ri,
+                                                                 (const double *)g_rj, (const double *)g_mh, (const double *)g_mu, (double *)out_rho, (double *)out_mu,
+                                                                 n[0], n[1]);
+    else
+        ela_backinterp_kernel<float><<<grid1d(nn), 256, 0, st>>>((const float *)rho, (const float *)mu, interp_rho, interp_mu, (const float *)g_ri, (const float *)g_rj,
+                                                                (const float *)g_mh, (const float *)g_mu, (float *)out_rho, (float *)out_mu, n[0], n[1]);
+    check_launch("ela_backinterp");
+    count_launch();
+}
+
 // L2 misfit with identity covariance on the device (L2Misfit.jl:24-77): r = syn - obs;
 // adjsrc = -r ; misfit += dot(r, r)/2 (accumulated in double)
 template <class T>

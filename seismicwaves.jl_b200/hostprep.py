@@ -143,26 +143,32 @@ def scale_stf_acoustic_vd(tf: np.ndarray, spacing: Sequence, dt, vp: np.ndarray,
 # ---- Kaiser-windowed sinc spreading (src/utils/utils.jl:71-214) -----------------------------------------
 
 
-def _kaiser(x: float, r: float, beta: float) -> float:
+def _kaiser(x, r, beta, T):
+    """kaiser(x, r, β) = besseli(0, β sqrt(1 - (x/r)^2)) / besseli(0, β) inside [-r, r], else 0.0 (utils.jl:71).
+    The reference evaluates it in T (SpecialFunctions.besseli has Float32 methods); scipy's i0 is evaluated in double and rounded to T."""
     from scipy.special import i0
 
     if -r <= x <= r:
-        return float(i0(beta * math.sqrt(1 - (x / r) ** 2)) / i0(beta))
+        q = T(x / r)
+        arg = T(beta * T(np.sqrt(T(T(1) - T(q * q)))))
+        return T(T(i0(float(arg))) / T(i0(float(beta))))
     return 0.0
 
 
-def _sinc(x: float) -> float:
+def _sinc(x, T):
+    x = T(x)
     if x == 0:
-        return 1.0
-    return math.sin(math.pi * x) / (math.pi * x)
+        return T(1)
+    px = T(T(np.pi) * x)
+    return T(np.sin(px) / px)
 
 
 def coeffsinc1d(x0, dx, nx: int, r: int, beta, xstart, mirror: bool, xbl, xbr, dtype):
-    """coeffsinc1D (utils.jl:105-154).  Returns (idxs, coeffs) with 1-based indices, duplicates summed,
-    in first-appearance order (the reference collects a Dict; order is irrelevant to the results)."""
+    """coeffsinc1D (utils.jl:105-154).  Returns (idxs, coeffs) with 1-based indices, duplicates summed, in ascending index
+    order (the reference collects the keys of a Dict, whose order is unspecified and irrelevant beyond rounding)."""
     T = np.dtype(dtype).type
     x0, dx, xstart, xbl, xbr, beta = T(x0), T(dx), T(xstart), T(xbl), T(xbr), T(beta)
-    xs = (xstart + np.arange(nx, dtype=np.float64) * np.float64(dx)).astype(T)  # range(xstart; length, step) evaluated in T
+    xs = (xstart + np.arange(nx, dtype=np.float64) * np.float64(dx)).astype(T)  # range(xstart; length, step): exact products rounded to T
 
     def findnearest(x):
         return int(np.argmin(np.abs(T(x) - xs))) + 1
@@ -170,23 +176,24 @@ def coeffsinc1d(x0, dx, nx: int, r: int, beta, xstart, mirror: bool, xbl, xbr, d
     i0_ = findnearest(x0)
     pts = []
     for idx in range(i0_ - r - 1, i0_ + r + 2):
-        xcurr = T(T(idx - 1) * dx + xstart)
-        coe = _kaiser(float(T(xcurr - x0)), float(T(T(r) * dx)), float(beta)) * _sinc(float(T(T(xcurr - x0) / dx)))
-        if not abs(coe) <= 1e-15:
+        xcurr = T(T(T(idx - 1) * dx) + xstart)
+        coe = _kaiser(T(xcurr - x0), T(T(r) * dx), beta, T) * _sinc(T(T(xcurr - x0) / dx), T)
+        if not abs(float(coe)) <= 1e-15:
             pts.append((idx, T(coe)))
     acc = {}
     for idx, coe in pts:
-        xcurr = T(T(idx - 1) * dx + xstart)
+        xcurr = T(T(T(idx - 1) * dx) + xstart)
         if xcurr < xbl:
             j = findnearest(T(xbl + T(xbl - xcurr)))
-            c = -coe if mirror else coe
+            c = T(-coe) if mirror else coe
         elif xcurr > xbr:
             j = findnearest(T(xbr - T(xcurr - xbr)))
-            c = -coe if mirror else coe
+            c = T(-coe) if mirror else coe
         else:
             j, c = idx, coe
         acc[j] = T(acc[j] + c) if j in acc else T(c)
-    return list(acc.keys()), [acc[k] for k in acc]
+    keys = sorted(acc)
+    return keys, [acc[k] for k in keys]
 
 
 def spread_positions(gridsize: Sequence[int], spacing: Sequence, positions: np.ndarray, shift: Sequence, mirror: bool, freesurfposition: str,

@@ -1,0 +1,120 @@
+"""GPU parity tests for the elastic P-SV path: CUDA engine (through the C ABI) vs the CPU oracle on identical seeded inputs.
+Tolerances: north-star rel-L2 <= 1e-5 (Float64) / 1e-4 (Float32); the reference-faithful arithmetic is expected to agree to
+rounding level, which the tighter bounds pin."""
+import numpy as np
+import pytest
+
+from cases import rel_l2, tol
+from elastic_cases import elastic_case, make_observed, oracle_forward, oracle_gradient
+
+pytestmark = pytest.mark.gpu
+
+
+def product_inputs(case, observed=None, check_freq=1, mute_src=0, mute_rec=0, fast_f32=False, snapevery=None):
+    import swb200 as S
+
+    T = case["dtype"].type
+    bc = S.CPMLBoundaryConditionParameters(halo=case["halo"], rcoef=T(case["rcoef"]), freeboundtop=case["freetop"])
+    params = S.InputParametersElastic(case["nt"], T(case["dt"]), case["n"], (T(case["h"]), T(case["h"])), bc, dtype=case["dtype"])
+    matprop = S.ElasticIsoMaterialProperties(case["rho"], case["lam"], case["mu"])
+    shots = []
+    for s in case["shots"]:
+        recs = S.VectorReceivers(s["rec_positions"].astype(T), case["nt"], dtype=case["dtype"])
+        if s["kind"] == "momten":
+            mts = [S.MomentTensor2D(*[T(v) for v in row]) for row in s["momtens"]]
+            srcs = S.MomentTensorSources(s["src_positions"].astype(T), s["src_tf"].astype(T), mts, T(s["domfreq"]))
+            shots.append(S.MomentTensorShot(srcs=srcs, recs=recs))
+        else:
+            srcs = S.ExternalForceSources(s["src_positions"].astype(T), s["src_tf"].astype(T), T(s["domfreq"]))
+            shots.append(S.ExternalForceShot(srcs=srcs, recs=recs))
+    runparams = S.RunParameters(parall="B200", fast_f32=fast_f32, snapevery=snapevery, erroronPPW=False)
+    gradparams = S.GradParameters(mute_radius_src=mute_src, mute_radius_rec=mute_rec, compute_misfit=True, check_freq=check_freq)
+    misfit = [S.L2Misfit(observed=o) for o in observed] if observed is not None else None
+    return params, matprop, shots, misfit, runparams, gradparams
+
+
+@pytest.mark.parametrize("kind", ["momten", "extforce"])
+@pytest.mark.parametrize("dtype,freetop,n", [(np.float64, True, (96, 80)), (np.float64, False, (83, 71)), (np.float32, True, (90, 77))])
+def test_forward_seismograms_match_oracle(kind, dtype, freetop, n):
+    import swb200 as S
+
+    case = elastic_case(n=n, nt=150, halo=7, freetop=freetop, dtype=dtype, kind=kind, nshots=2, nsrc=2, nrec=5, seed=13)
+    ref, _ = oracle_forward(case)
+    params, matprop, shots, _, runparams, _ = product_inputs(case)
+    S.swforward(params, matprop, shots, runparams=runparams)
+    for r, sh in zip(ref, shots):
+        g = sh.recs.seismograms
+        assert g.dtype == np.dtype(dtype) and np.max(np.abs(r)) > 0
+        err = rel_l2(g, r)
+        assert err <= tol(dtype), err
+        assert err <= (1e-12 if dtype == np.float64 else 2e-6), err
+
+
+@pytest.mark.parametrize("kind,dtype,check_freq", [("momten", np.float64, 1), ("momten", np.float64, 7), ("extforce", np.float64, 10), ("extforce", np.float32, 9),
+                                                   ("momten", np.float32, 1)])
+def test_gradient_and_misfit_match_oracle(kind, dtype, check_freq):
+    import swb200 as S
+
+    case = elastic_case(n=(72, 64), nt=100, halo=6, dtype=dtype, kind=kind, nshots=2, nrec=4, seed=17 + check_freq)
+    syn, _ = oracle_forward(case)
+    obs = make_observed(case, syn)
+    (gref, mref), sref = oracle_gradient(case, obs, check_freq=check_freq, mute_src=3, mute_rec=1)
+    params, matprop, shots, misfit, runparams, gradparams = product_inputs(case, observed=obs, check_freq=check_freq, mute_src=3, mute_rec=1)
+    ggot, mgot = S.swgradient(params, matprop, shots, misfit, runparams=runparams, gradparams=gradparams)
+    assert set(ggot) == {"rho", "lambda", "mu"}
+    for k in gref:
+        assert np.max(np.abs(gref[k])) > 0
+        err = rel_l2(ggot[k], gref[k])
+        assert err <= tol(dtype), (k, err)
+        assert err <= (1e-10 if dtype == np.float64 else 5e-5), (k, err)
+    assert abs(float(mgot) - float(mref)) <= tol(dtype) * abs(float(mref))
+    for r, sh in zip(sref, shots):
+        assert rel_l2(sh.recs.seismograms, r) <= tol(dtype)
+
+
+def test_checkpointed_equals_non_checkpointed_gradient():
+    """reference test: test/test_gradient_elastic_homogeneous.jl:62-119"""
+    import swb200 as S
+
+    case = elastic_case(n=(80, 64), nt=121, halo=6, kind="extforce", seed=4, nrec=3)
+    syn, _ = oracle_forward(case)
+    obs = make_observed(case, syn)
+    out = []
+    for cf in (1, 11):
+        params, matprop, shots, misfit, runparams, gradparams = product_inputs(case, observed=obs, check_freq=cf)
+        out.append(S.swgradient(params, matprop, shots, misfit, runparams=runparams, gradparams=gradparams))
+    for k in ("rho", "lambda", "mu"):
+        assert np.array_equal(out[0][0][k], out[1][0][k])
+    assert out[0][1] == out[1][1]
+
+
+def test_fast_f32_within_tolerance():
+    import swb200 as S
+
+    case = elastic_case(n=(96, 80), nt=300, halo=8, dtype=np.float32, kind="momten", seed=6)
+    ref, _ = oracle_forward(case)
+    params, matprop, shots, _, runparams, _ = product_inputs(case, fast_f32=True)
+    S.swforward(params, matprop, shots, runparams=runparams)
+    assert rel_l2(shots[0].recs.seismograms, ref[0]) <= tol(np.float32)
+
+
+def test_nearest_grid_point_sources_and_snapshots():
+    """sincinterp = false path (ela_models.jl:31-45) and the ucur / σ snapshots (ela_forward.jl:64-67)"""
+    import swb200 as S
+    from oracle import oracle as O
+    from elastic_cases import matprops, oracle_shots, params_oracle
+
+    case = elastic_case(n=(64, 60), nt=60, halo=6, kind="extforce", seed=8, nrec=3)
+    sim = O.build_wavesim("elastic_iso", params_oracle(case), sincinterp=False)
+    oshots = oracle_shots(case)
+    snaps_ref = O.swforward(sim, matprops(case), oshots, snapevery=20)
+    params, matprop, shots, _, runparams, _ = product_inputs(case, snapevery=20)
+    ws = S.build_wavesim(params, matprop, runparams=runparams, sincinterp=False)
+    snaps = S.swforward(ws, matprop, shots)
+    assert rel_l2(shots[0].recs.seismograms, oshots[0].seismograms) <= 1e-12
+    assert sorted(snaps[0].keys()) == [20, 40, 60]
+    for it in (20, 40, 60):
+        for c in range(2):
+            assert rel_l2(snaps[0][it]["ucur"][c], snaps_ref[0][it]["ucur"][c]) <= 1e-12
+        for c in range(3):
+            assert rel_l2(snaps[0][it]["σ"][c], snaps_ref[0][it]["sigma"][c]) <= 1e-12
