@@ -1,0 +1,505 @@
+// acou_cd_fused.cu -- fused acoustic constant-density time step (2D and 3D) for the per-shot engine.
+//
+// One step of the reference is five or six launches (src/models/acoustic/backends/shared/acoustic2D_xPU.jl:1-126,
+// acoustic3D_xPU.jl:1-219):
+//     psi_d <- b_h psi_d + a_h d_d p            update_ψ_x! / _y! / _z!   (C-PML strips, from pcur)
+//     xi_d  <- b xi_d + a (d2_d p + d_d psi_d)  inside update_p_CPML!      (src/utils/fdgen.jl:163-193)
+//     pnew  <- 2.0 pcur - pold + fact * lap~    update_p_CPML!
+//     pnew[src] += tf[it, s]                    inject_sources!
+//     traces[it, r] = pnew[rec]                 record_receivers!
+// plus, in the gradient's adjoint loop, the zero-lag correlation of the freshly updated adjoint field with the
+// stored forward fields, grad += adj * (p_itm2 - 2.0 p_itm1 + p_it) / dt^2 (correlate_gradient_xPU.jl:1-10).
+// Here a step is two kernels that write disjoint cells, read only the previous time levels and therefore run
+// concurrently (the engine forks the rim kernel onto a second stream inside its CUDA graph):
+//
+//  * cd_bulk_kernel -- every 16-byte vector of cells that lies outside the C-PML strips and off the grid faces
+//    (85 % of a 768^3 grid with halo 20, 98 % of 4096^2).  2.5D register-queue march: a thread owns V = 16 bytes /
+//    sizeof(T) consecutive x cells of one (x, y) column position and marches along z over `zc` planes with
+//    p[k-1], p[k], p[k+1] in registers; a warp owns one 32 V cell row.  x neighbours come from the adjacent lanes
+//    with warp shuffles (lanes 0 / 31 fetch the one halo column each); y neighbours are read through L1 (they are
+//    the lines the neighbouring warps of the CTA brought in as their own centre values one iteration earlier), so
+//    there is no shared-memory staging and no barrier and warps drift freely; z neighbours come from the queue.
+//    The loads of iteration k+1 (pcur[k+2], pold[k+1], fact[k+1], halo column) are issued before the arithmetic of
+//    iteration k.  HBM traffic per cell-update: pcur, pold, fact read, pnew written = 4 values; adjoint +
+//    correlation adds p_itm2, p_itm1, p_it read and grad read + written = 9 values.
+//  * cd_rim_kernel -- the strips and faces, enumerated compactly as up to six boxes of vectors, one thread per
+//    vector, generic code: a cell in a strip recomputes the two psi values its d_d psi needs from (psi_old, pcur)
+//    instead of reading what a separate psi sweep stored, so psi is double-buffered; xi has exactly one owner per
+//    entry and is updated in place.  Cells on the grid faces are never updated by the reference (pnew aliases pold
+//    there); here they copy pold so that pnew may live anywhere.
+// The values are those of the reference sequence operation for operation (SWB_FLAG_FAST_F32 swaps in FMA forms).
+// A 2D grid (nx, ny) is run as (nx, 1, ny): no y term, every warp of a bulk CTA marches on its own x range.
+#include "cd_fused.h"
+#include "kernels.h"
+
+namespace swb {
+
+namespace {
+
+template <class T, int V>
+struct alignas(16) CVec {
+    T v[V];
+};
+
+template <class T, int V>
+__device__ __forceinline__ CVec<T, V> ldv(const T *p)
+{
+    return *reinterpret_cast<const CVec<T, V> *>(p);
+}
+template <class T, int V>
+__device__ __forceinline__ void stv(T *p, const CVec<T, V> &c)
+{
+    *reinterpret_cast<CVec<T, V> *>(p) = c;
+}
+
+__device__ __forceinline__ float shfl_up1(float x) { return __shfl_up_sync(0xffffffffu, x, 1); }
+__device__ __forceinline__ float shfl_dn1(float x) { return __shfl_down_sync(0xffffffffu, x, 1); }
+__device__ __forceinline__ double shfl_up1(double x) { return __shfl_up_sync(0xffffffffu, x, 1); }
+__device__ __forceinline__ double shfl_dn1(double x) { return __shfl_down_sync(0xffffffffu, x, 1); }
+
+// plain second difference (lo - 2 mid + hi) / d^2: reference order with the Fornberg weights (fdgen.jl:96-131), or FMA form
+template <class CT, bool FMA>
+__device__ __forceinline__ CT d2(const CT (&w)[3], CT lo, CT mid, CT hi, CT inv2)
+{
+    if (FMA)
+        return (fma((CT)-2.0, mid, lo) + hi) * inv2;
+    return ((w[0] * lo + w[1] * mid) + w[2] * hi) * inv2;
+}
+
+// pnew = 2.0 pcur - pold + fact * lap  (acoustic2D_xPU.jl:43)
+template <class T, class CT, bool FMA>
+__device__ __forceinline__ T leapfrog(CT pc, T po, T fc, CT lap)
+{
+    if (FMA)
+        return (T)fma((CT)fc, lap, fma((CT)2.0, pc, -(CT)po));
+    return (T)((((CT)2.0 * pc) - (CT)po) + (CT)fc * lap);
+}
+
+// grad + adj * (pm2 - 2.0 pm1 + p0) * _dt2  (correlate_gradient_xPU.jl:1-10)
+template <class T, class CT, bool FMA>
+__device__ __forceinline__ T correlate(T g, T adj, T pm2, T pm1, T p0, T inv_dt2)
+{
+    if (FMA) {
+        const CT lapt = fma((CT)-2.0, (CT)pm1, (CT)pm2) + (CT)p0;
+        return (T)fma((CT)adj * lapt, (CT)inv_dt2, (CT)g);
+    }
+    const CT lapt = ((CT)pm2 - (CT)2.0 * (CT)pm1) + (CT)p0;
+    return (T)((CT)g + ((CT)adj * lapt) * (CT)inv_dt2);
+}
+
+// point sources / receivers of this CTA touching the vector whose first cell has in-CTA code `code0`
+template <class T, int V>
+__device__ __forceinline__ void inject_points(const CdFusedParams<T> &P, const CdPointList &L, int cta, int code0, CVec<T, V> &out)
+{
+    const int e0 = L.off[cta], e1 = L.off[cta + 1];
+    for (int e = e0; e < e1; ++e) { // entries in source-index order: summed like the CPU loop
+        const int d = L.cell[e] - code0;
+        if (d >= 0 && d < V) {
+            const T s = P.inj_tf[(long long)L.idx[e] * P.inj_nt + (P.inj_it - 1)];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (v == d)
+                    out.v[v] = out.v[v] + s;
+        }
+    }
+}
+template <class T, int V>
+__device__ __forceinline__ void record_points(const CdFusedParams<T> &P, const CdPointList &L, int cta, int code0, const CVec<T, V> &out)
+{
+    const int e0 = L.off[cta], e1 = L.off[cta + 1];
+    for (int e = e0; e < e1; ++e) {
+        const int d = L.cell[e] - code0;
+        if (d >= 0 && d < V) {
+            T val = (T)0;
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (v == d)
+                    val = out.v[v];
+            P.traces[(long long)L.idx[e] * P.rec_nt + (P.rec_it - 1)] = val;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// bulk kernel
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
+__global__ void __launch_bounds__(HAS_Y ? 32 * CDF_TY : 32 * CDF_W2D, HAS_Y ? (sizeof(CT) == 4 ? (ADJ ? 3 : 4) : 2) : (sizeof(CT) == 4 ? 8 : 4))
+    cd_bulk_kernel(const CdFusedParams<T> P)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int TX = 32 * V;
+    constexpr int TY = HAS_Y ? CDF_TY : 1;
+    typedef CVec<T, V> VT;
+
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    const int xt = HAS_Y ? (int)blockIdx.x : (int)(blockIdx.x * blockDim.y) + ty;
+    const int i0 = xt * TX + lane * V;
+    const int j = HAS_Y ? P.jlo + (int)blockIdx.y * TY + ty : 0;
+    if (xt * TX >= P.nx || j >= P.jhi)
+        return; // warps are independent (no barriers); a warp leaves only as a whole (shuffles below)
+    const int k0 = P.klo + (int)blockIdx.z * P.zc, k1 = min(k0 + P.zc, P.khi);
+    const int iv = xt * 32 + lane;
+    const bool ld_ok = i0 < P.nx;                   // this lane's vector exists: it feeds the neighbours' shuffles
+    const bool st_ok = iv >= P.ivlo && iv < P.ivhi; // this lane's vector belongs to the bulk
+    const bool hx_any = st_ok && (lane == 0 || lane == 31);
+    const long long ld = P.ld, plane = P.plane;
+    long long off = (long long)k0 * plane + (long long)j * ld + i0; // this thread's vector in plane k
+    const long long hxo = lane == 0 ? -1 : V;
+    const int cta = ((int)blockIdx.z * (int)gridDim.y + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x;
+    const bool has_inj = P.inj_it > 0 && P.inj[0].off[cta + 1] > P.inj[0].off[cta];
+    const bool has_rec = P.rec_it > 0 && P.rec[0].off[cta + 1] > P.rec[0].off[cta];
+
+    const CT w2[3] = {(CT)P.c2[0], (CT)P.c2[1], (CT)P.c2[2]};
+    const CT i2x = (CT)(P.inv_d[0] * P.inv_d[0]), i2y = (CT)(P.inv_d[1] * P.inv_d[1]), i2z = (CT)(P.inv_d[2] * P.inv_d[2]);
+
+    CT pm[V], pc[V], pp[V], hxc = (CT)0;
+    VT po = {}, fc = {};
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        pm[v] = pc[v] = pp[v] = (CT)0;
+    // ---- prologue: fill the queue for plane k0 (bulk planes always have both z neighbours) ----------------------------
+    if (ld_ok) {
+        const VT a = ldv<T, V>(P.pcur + off - plane), b = ldv<T, V>(P.pcur + off), c = ldv<T, V>(P.pcur + off + plane);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            pm[v] = (CT)a.v[v];
+            pc[v] = (CT)b.v[v];
+            pp[v] = (CT)c.v[v];
+        }
+    }
+    if (st_ok) {
+        po = ldv<T, V>(P.pold + off);
+        fc = ldv<T, V>(P.fact + off);
+    }
+    if (hx_any)
+        hxc = (CT)P.pcur[off + hxo];
+
+#pragma unroll 1
+    for (int k = k0; k < k1; ++k) {
+        // ---- loads: the next iteration's centre / pold / fact / halo column, this iteration's y neighbours (L1) -------
+        const bool more = k + 1 < k1;
+        VT pn = {}, po_n = {}, fc_n = {}, yu = {}, yd = {};
+        T hx_n = (T)0;
+        if (ld_ok && more)
+            pn = ldv<T, V>(P.pcur + off + 2 * plane);
+        if (st_ok) {
+            if (HAS_Y) {
+                yu = ldv<T, V>(P.pcur + off - ld);
+                yd = ldv<T, V>(P.pcur + off + ld);
+            }
+            if (more) {
+                po_n = ldv<T, V>(P.pold + off + plane);
+                fc_n = ldv<T, V>(P.fact + off + plane);
+            }
+        }
+        if (hx_any && more)
+            hx_n = P.pcur[off + plane + hxo];
+        VT c2 = {}, c1 = {}, c0 = {}, g = {};
+        if (ADJ && st_ok) {
+            c2 = ldv<T, V>(P.pm2 + off);
+            c1 = ldv<T, V>(P.pm1 + off);
+            c0 = ldv<T, V>(P.p0 + off);
+            g = ldv<T, V>(P.grad + off);
+        }
+        CT xl_in = shfl_up1(pc[V - 1]);
+        CT xr_in = shfl_dn1(pc[0]);
+        if (lane == 0)
+            xl_in = hxc;
+        if (lane == 31)
+            xr_in = hxc;
+        if (st_ok) {
+            VT out;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const CT xl = v > 0 ? pc[v > 0 ? v - 1 : 0] : xl_in;
+                const CT xr = v < V - 1 ? pc[v < V - 1 ? v + 1 : 0] : xr_in;
+                CT lap = d2<CT, FMA>(w2, xl, pc[v], xr, i2x);
+                if (HAS_Y)
+                    lap = lap + d2<CT, FMA>(w2, (CT)yu.v[v], pc[v], (CT)yd.v[v], i2y);
+                lap = lap + d2<CT, FMA>(w2, pm[v], pc[v], pp[v], i2z);
+                out.v[v] = leapfrog<T, CT, FMA>(pc[v], po.v[v], fc.v[v], lap);
+            }
+            const int code0 = ((k - k0) * (int)blockDim.y + ty) * TX + lane * V;
+            if (has_inj)
+                inject_points<T, V>(P, P.inj[0], cta, code0, out);
+            stv<T, V>(P.pnew + off, out);
+            if (has_rec)
+                record_points<T, V>(P, P.rec[0], cta, code0, out);
+            if (ADJ) {
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    g.v[v] = correlate<T, CT, FMA>(g.v[v], out.v[v], c2.v[v], c1.v[v], c0.v[v], P.inv_dt2);
+                stv<T, V>(P.grad + off, g);
+            }
+        }
+        // ---- rotate the queue ------------------------------------------------------------------------------------------
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            pm[v] = pc[v];
+            pc[v] = pp[v];
+            pp[v] = (CT)pn.v[v];
+        }
+        po = po_n;
+        fc = fc_n;
+        hxc = (CT)hx_n;
+        off += plane;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// rim kernel
+// ---------------------------------------------------------------------------------------------------------------------
+
+// One axis of @∇̃² for an interior cell (fdgen.jl:163-193 with the psi update of acoustic2D_xPU.jl:1-25 inlined).
+//   lo, mid, hi : p at c-1, c, c+1 along the axis;  c1b: 1-based index of the cell along the axis;  n: axis extent
+//   entry ii (1-based) of psi lives at psi[(ii-1)*stride] (base pointers already offset to this cell's line)
+template <class T, class CT, bool FMA>
+__device__ __forceinline__ CT cd_axis_term(const CT (&w1)[2], const CT (&w2)[3], CT lo, CT mid, CT hi, int c1b, int n, int h, T inv, const T *__restrict__ a,
+                                           const T *__restrict__ b, const T *__restrict__ a_h, const T *__restrict__ b_h, const T *__restrict__ psi_in,
+                                           T *__restrict__ psi_out, T *__restrict__ xi, long long stride)
+{
+    const CT D2 = d2<CT, FMA>(w2, lo, mid, hi, (CT)(inv * inv));
+    int ii;
+    if (c1b <= h)
+        ii = c1b;
+    else if (c1b >= n - h + 1)
+        ii = c1b - (n - h) + 1 + h;
+    else
+        return D2;
+    // psi[ii] belongs to grid cell c (difference p[c+1]-p[c]), psi[ii-1] to cell c-1
+    const CT Dhi = (w1[0] * mid + w1[1] * hi) * (CT)inv;
+    const CT Dlo = (w1[0] * lo + w1[1] * mid) * (CT)inv;
+    T psi_hi, psi_lo;
+    (void)cpml_apply<T, CT>(Dhi, a_h[ii - 1], b_h[ii - 1], psi_in[(long long)(ii - 1) * stride], psi_hi);
+    (void)cpml_apply<T, CT>(Dlo, a_h[ii - 2], b_h[ii - 2], psi_in[(long long)(ii - 2) * stride], psi_lo);
+    psi_out[(long long)(ii - 1) * stride] = psi_hi;
+    if (c1b == 2 || c1b == n - h + 1) // the strip's first entry has no interior cell of its own
+        psi_out[(long long)(ii - 2) * stride] = psi_lo;
+    const CT dpsi = (w1[0] * (CT)psi_lo + w1[1] * (CT)psi_hi) * (CT)inv;
+    T *x = xi + (long long)(ii - 1) * stride;
+    const T bx = b[ii - 1] * *x;
+    const T xn = (T)((CT)bx + (CT)a[ii - 1] * (D2 + dpsi));
+    *x = xn;
+    return (D2 + dpsi) + (CT)xn;
+}
+
+template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
+__global__ void __launch_bounds__(CDF_RIM_T) cd_rim_kernel(const CdFusedParams<T> P)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    typedef CVec<T, V> VT;
+    const long long vid = (long long)blockIdx.x * CDF_RIM_T + threadIdx.x;
+    if (vid >= P.nrimvec)
+        return;
+    int bi = 0;
+#pragma unroll
+    for (int b = 1; b < CDF_MAX_BOX; ++b)
+        if (b < P.nbox && vid >= P.box[b].start)
+            bi = b;
+    const CdBox &B = P.box[bi];
+    const long long loc = vid - B.start;
+    const int iv = B.iv0 + (int)(loc % B.nvx);
+    const long long r = loc / B.nvx;
+    const int j = B.j0 + (int)(r % B.ny), k = B.k0 + (int)(r / B.ny);
+    const int i0 = iv * V;
+    const int nx = P.nx, ny = P.ny, nz = P.nz, h = P.halo;
+    const long long ld = P.ld, plane = P.plane;
+    const long long off = (long long)k * plane + (long long)j * ld + i0;
+
+    VT out = ldv<T, V>(P.pold + off); // faces (and pitch padding) keep pold
+    const bool y_int = !HAS_Y || (j >= 1 && j <= ny - 2);
+    const bool z_int = k >= 1 && k <= nz - 2;
+    if (y_int && z_int) {
+        const VT pcv = ldv<T, V>(P.pcur + off), fcv = ldv<T, V>(P.fact + off);
+        const VT zm = ldv<T, V>(P.pcur + off - plane), zp = ldv<T, V>(P.pcur + off + plane);
+        VT yu = {}, yd = {};
+        if (HAS_Y) {
+            yu = ldv<T, V>(P.pcur + off - ld);
+            yd = ldv<T, V>(P.pcur + off + ld);
+        }
+        const T xl_in = i0 > 0 ? P.pcur[off - 1] : (T)0;
+        const T xr_in = i0 + V < nx ? P.pcur[off + V] : (T)0;
+        const CT w1[2] = {(CT)P.c1[0], (CT)P.c1[1]};
+        const CT w2[3] = {(CT)P.c2[0], (CT)P.c2[1], (CT)P.c2[2]};
+        const long long jk = (long long)k * ny + j; // line index for the x-strip arrays
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int i = i0 + v;
+            if (i < 1 || i > nx - 2)
+                continue;
+            const CT pc = (CT)pcv.v[v];
+            const CT xl = (CT)(v > 0 ? pcv.v[v > 0 ? v - 1 : 0] : xl_in);
+            const CT xr = (CT)(v < V - 1 ? pcv.v[v < V - 1 ? v + 1 : 0] : xr_in);
+            CT lap = cd_axis_term<T, CT, FMA>(w1, w2, xl, pc, xr, i + 1, nx, h, P.inv_d[0], P.a[0], P.b[0], P.a_h[0], P.b_h[0], P.psi_in[0] + jk * (2 * h),
+                                              P.psi_out[0] + jk * (2 * h), P.xi[0] + jk * (2 * (h + 1)), 1);
+            if (HAS_Y)
+                lap = lap + cd_axis_term<T, CT, FMA>(w1, w2, (CT)yu.v[v], pc, (CT)yd.v[v], j + 1, ny, h, P.inv_d[1], P.a[1], P.b[1], P.a_h[1], P.b_h[1],
+                                                     P.psi_in[1] + (long long)k * nx * (2 * h) + i, P.psi_out[1] + (long long)k * nx * (2 * h) + i,
+                                                     P.xi[1] + (long long)k * nx * (2 * (h + 1)) + i, nx);
+            lap = lap + cd_axis_term<T, CT, FMA>(w1, w2, (CT)zm.v[v], pc, (CT)zp.v[v], k + 1, nz, h, P.inv_d[2], P.a[2], P.b[2], P.a_h[2], P.b_h[2],
+                                                 P.psi_in[2] + (long long)j * nx + i, P.psi_out[2] + (long long)j * nx + i, P.xi[2] + (long long)j * nx + i,
+                                                 (long long)nx * ny);
+            out.v[v] = leapfrog<T, CT, FMA>(pc, out.v[v], fcv.v[v], lap);
+        }
+    }
+    const int cta = (int)blockIdx.x, code0 = (int)threadIdx.x * V;
+    if (P.inj_it > 0)
+        inject_points<T, V>(P, P.inj[1], cta, code0, out);
+    stv<T, V>(P.pnew + off, out);
+    if (P.rec_it > 0)
+        record_points<T, V>(P, P.rec[1], cta, code0, out);
+    if (ADJ) {
+        const VT c2 = ldv<T, V>(P.pm2 + off), c1 = ldv<T, V>(P.pm1 + off), c0 = ldv<T, V>(P.p0 + off);
+        VT g = ldv<T, V>(P.grad + off);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            g.v[v] = correlate<T, CT, FMA>(g.v[v], out.v[v], c2.v[v], c1.v[v], c0.v[v], P.inv_dt2);
+        stv<T, V>(P.grad + off, g);
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool has_y, int zc)
+{
+    CdFusedGeom g{};
+    g.v = cdf_vec(esize);
+    g.tx = cdf_tx(esize);
+    g.has_y = has_y;
+    g.ty = has_y ? CDF_TY : CDF_W2D;
+    g.nx = nx, g.ny = ny, g.nz = nz;
+    g.hs = std::max(halo, 1);
+    g.zc = zc;
+    const int nvec = (int)(cdf_ld(nx, esize) / g.v);
+    g.ivlo = (g.hs + g.v - 1) / g.v;
+    g.ivhi = std::max(g.ivlo, (nx - g.hs) / g.v);
+    g.jlo = has_y ? g.hs : 0;
+    g.jhi = has_y ? std::max(g.jlo, ny - g.hs) : 1;
+    g.klo = g.hs;
+    g.khi = std::max(g.klo, nz - g.hs);
+    g.ntx = (nx + g.tx - 1) / g.tx;
+    g.nty = has_y ? (g.jhi - g.jlo + CDF_TY - 1) / CDF_TY : 1;
+    g.ntz = (g.khi - g.klo + zc - 1) / zc;
+    g.gx = has_y ? (unsigned)g.ntx : (unsigned)((g.ntx + CDF_W2D - 1) / CDF_W2D);
+    g.gy = (unsigned)g.nty;
+    g.gz = (unsigned)g.ntz;
+    if (g.ivhi <= g.ivlo || g.nty == 0 || g.ntz == 0)
+        g.gx = g.gy = g.gz = 0;
+    // rim boxes: z slabs, then y slabs between them, then x slabs inside both
+    long long start = 0;
+    auto add = [&](int iv0, int nvx, int j0, int nyb, int k0, int nzb) {
+        if (nvx <= 0 || nyb <= 0 || nzb <= 0)
+            return;
+        CdBox &b = g.box[g.nbox++];
+        b.iv0 = iv0, b.j0 = j0, b.k0 = k0, b.nvx = nvx, b.ny = nyb, b.nz = nzb, b.start = start;
+        start += (long long)nvx * nyb * nzb;
+    };
+    const int zlo = std::min(g.klo, nz), zhi = std::max(g.khi, zlo); // planes [0, zlo) and [zhi, nz) are rim
+    add(0, nvec, 0, ny, 0, zlo);
+    add(0, nvec, 0, ny, zhi, nz - zhi);
+    if (has_y) {
+        const int ylo = std::min(g.jlo, ny), yhi = std::max(g.jhi, ylo);
+        add(0, nvec, 0, ylo, zlo, zhi - zlo);
+        add(0, nvec, yhi, ny - yhi, zlo, zhi - zlo);
+    }
+    add(0, g.ivlo, g.jlo, g.jhi - g.jlo, zlo, zhi - zlo);
+    add(g.ivhi, nvec - g.ivhi, g.jlo, g.jhi - g.jlo, zlo, zhi - zlo);
+    g.nrimvec = start;
+    return g;
+}
+
+int cd_fused_locate(const CdFusedGeom &g, int i, int j, int k, int *cta, int *code)
+{
+    const int iv = i / g.v;
+    const bool bulk = g.gx > 0 && iv >= g.ivlo && iv < g.ivhi && j >= g.jlo && j < g.jhi && k >= g.klo && k < g.khi;
+    if (bulk) {
+        const int xt = i / g.tx, xl = i % g.tx;
+        const int bz = (k - g.klo) / g.zc, kl = (k - g.klo) % g.zc;
+        int bx, by, ty;
+        if (g.has_y) {
+            bx = xt;
+            by = (j - g.jlo) / CDF_TY;
+            ty = (j - g.jlo) % CDF_TY;
+        } else {
+            bx = xt / CDF_W2D;
+            by = 0;
+            ty = xt % CDF_W2D;
+        }
+        *cta = (bz * (int)g.gy + by) * (int)g.gx + bx;
+        *code = (kl * g.ty + ty) * g.tx + xl;
+        return 0;
+    }
+    for (int b = 0; b < g.nbox; ++b) {
+        const CdBox &B = g.box[b];
+        if (iv >= B.iv0 && iv < B.iv0 + B.nvx && j >= B.j0 && j < B.j0 + B.ny && k >= B.k0 && k < B.k0 + B.nz) {
+            const long long lin = B.start + ((long long)(k - B.k0) * B.ny + (j - B.j0)) * B.nvx + (iv - B.iv0);
+            *cta = (int)(lin / CDF_RIM_T);
+            *code = (int)(lin % CDF_RIM_T) * g.v + i % g.v;
+            return 1;
+        }
+    }
+    throw Error(SWB_ERR_STATE, "fused CD geometry: cell belongs to neither the bulk nor the rim");
+}
+
+template <class T>
+void cd_fused_fill_geom(CdFusedParams<T> &P, const CdFusedGeom &g)
+{
+    P.jlo = g.jlo, P.jhi = g.jhi, P.klo = g.klo, P.khi = g.khi, P.ivlo = g.ivlo, P.ivhi = g.ivhi, P.zc = g.zc;
+    P.nbox = g.nbox;
+    for (int b = 0; b < g.nbox; ++b)
+        P.box[b] = g.box[b];
+    P.nrimvec = g.nrimvec;
+}
+
+template <class T>
+void cd_fused_launch(const CdFusedParams<T> &P, const CdFusedGeom &g, bool adj, bool fast, cudaStream_t st, cudaStream_t st_rim)
+{
+    SWB_REQUIRE(g.gy <= 65535 && g.gz <= 65535, "grid too large for the fused CD launch geometry");
+    const dim3 grd(g.gx, g.gy, g.gz), blk(32, g.ty, 1);
+    const unsigned nrim = (unsigned)g.ncta_rim();
+    const bool f32fast = sizeof(T) == 4 && fast, has_y = g.has_y;
+#define SWB_CDF_GO(CT, HY, AD, FM)                                                      \
+    do {                                                                                \
+        if (g.gx > 0) {                                                                 \
+            cd_bulk_kernel<T, CT, HY, AD, FM><<<grd, blk, 0, st>>>(P);                  \
+            check_launch("cd_bulk_kernel");                                             \
+            count_launch();                                                             \
+        }                                                                               \
+        if (nrim > 0) {                                                                 \
+            cd_rim_kernel<T, CT, HY, AD, FM><<<nrim, CDF_RIM_T, 0, st_rim>>>(P);        \
+            check_launch("cd_rim_kernel");                                              \
+            count_launch();                                                             \
+        }                                                                               \
+    } while (0)
+#define SWB_CDF_CT(CT, FM)                    \
+    do {                                      \
+        if (has_y) {                          \
+            if (adj)                          \
+                SWB_CDF_GO(CT, true, true, FM);   \
+            else                              \
+                SWB_CDF_GO(CT, true, false, FM);  \
+        } else {                              \
+            if (adj)                          \
+                SWB_CDF_GO(CT, false, true, FM);  \
+            else                              \
+                SWB_CDF_GO(CT, false, false, FM); \
+        }                                     \
+    } while (0)
+    if (f32fast)
+        SWB_CDF_CT(T, true);
+    else
+        SWB_CDF_CT(double, false);
+#undef SWB_CDF_CT
+#undef SWB_CDF_GO
+}
+
+template void cd_fused_fill_geom<float>(CdFusedParams<float> &, const CdFusedGeom &);
+template void cd_fused_fill_geom<double>(CdFusedParams<double> &, const CdFusedGeom &);
+template void cd_fused_launch<float>(const CdFusedParams<float> &, const CdFusedGeom &, bool, bool, cudaStream_t, cudaStream_t);
+template void cd_fused_launch<double>(const CdFusedParams<double> &, const CdFusedGeom &, bool, bool, cudaStream_t, cudaStream_t);
+
+} // namespace swb

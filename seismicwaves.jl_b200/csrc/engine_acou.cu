@@ -7,6 +7,7 @@
 // the seismograms and (optionally) the adjoint source.
 #include "engine.h"
 #include "vd_fused.h"
+#include "cd_fused.h"
 #include <cstring>
 
 namespace swb {
@@ -16,22 +17,28 @@ namespace swb {
 // =====================================================================================================
 class AcousticCD : public SimBase {
   public:
-    explicit AcousticCD(const swb_sim_desc &d) : SimBase(d)
+    // own_state = false: a subclass keeps the wavefield state in its own layout (fused engine below)
+    explicit AcousticCD(const swb_sim_desc &d, bool own_state = true) : SimBase(d)
     {
         SWB_REQUIRE(d.ndim == 2 || d.ndim == 3, "acoustic constant-density engine supports N = 2, 3");
         const size_t nb = ncells() * esize;
         fact_ = dalloc(nb);
         vp_ = dalloc(nb);
-        for (int k = 0; k < 3; ++k)
-            p_[k] = dalloc(nb);
-        alloc_mem(psi_, xi_);
+        if (own_state) {
+            for (int k = 0; k < 3; ++k)
+                p_[k] = dalloc(nb);
+            alloc_mem(psi_, xi_);
+        }
         if (d.gradient) {
             grad_ = dalloc(nb);
             work_ = dalloc(nb);
+            total_grad_.push_back(dalloc(nb));
+            misfit_acc_ = dalloc(sizeof(double));
+        }
+        if (d.gradient && own_state) {
             for (int k = 0; k < 3; ++k)
                 adj_[k] = dalloc(nb);
             alloc_mem(psi_adj_, xi_adj_);
-            total_grad_.push_back(dalloc(nb));
             std::vector<DeviceCheckpointer::FieldSpec> fs(3);
             fs[0].comp_bytes = {nb};
             fs[0].width = 2;
@@ -42,7 +49,6 @@ class AcousticCD : public SimBase {
             }
             ckpt_.reset(new DeviceCheckpointer(d.nt, d.check_freq, fs, stream));
             dev_bytes_ += (int64_t)ckpt_->bytes();
-            misfit_acc_ = dalloc(sizeof(double));
         }
         sync();
     }
@@ -155,7 +161,7 @@ class AcousticCD : public SimBase {
         download(host_out, src, b);
     }
 
-  private:
+  protected:
     void alloc_mem(DevBuf (&psi)[3], DevBuf (&xi)[3])
     {
         for (int ax = 0; ax < desc.ndim; ++ax) {
@@ -187,7 +193,7 @@ class AcousticCD : public SimBase {
     }
 
     // reset! (acou_models.jl:221-226): zero every field except fact
-    void begin_shot()
+    virtual void begin_shot()
     {
         use_device();
         SWB_REQUIRE(mat_set_, "material properties not set");
@@ -294,7 +300,7 @@ class AcousticCD : public SimBase {
     }
 
     // adjoint loop with re-forwarding and correlation (acou_gradient.jl:50-82)
-    void adjoint_loop()
+    virtual void adjoint_loop()
     {
         const size_t nb = ncells() * esize;
         prescale_residuals(desc.dtype, desc.ndim, desc.n, adjsrc_.p, desc.nt, nrec_, posrec_.as<int64_t>(), fact_.p, stream);
@@ -339,7 +345,15 @@ class AcousticCD : public SimBase {
     bool mat_set_ = false;
 };
 
-SimBase *make_acoustic_cd(const swb_sim_desc &d) { return new AcousticCD(d); }
+#include "engine_cd_fused.inc"
+
+SimBase *make_acoustic_cd(const swb_sim_desc &d)
+{
+    // the fused single-launch engine is the default; SWB_FLAG_NO_FUSION selects the one-launch-per-reference-kernel path
+    if (!(d.flags & SWB_FLAG_NO_FUSION))
+        return new AcousticCDFused(d);
+    return new AcousticCD(d);
+}
 
 // =====================================================================================================
 // Acoustic variable density, staggered (2D)

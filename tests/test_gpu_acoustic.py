@@ -232,3 +232,74 @@ def test_vd_fused_snapshots_match_oracle():
     assert sorted(snaps[0].keys()) == [20, 40, 60]
     for it in (20, 40, 60):
         assert rel_l2(snaps[0][it]["pcur"], snaps_ref[0][it]) <= 1e-12
+
+
+# ---- fused constant-density engine (2D and 3D register-queue march) on grids spanning many tiles / z chunks -----------------
+
+
+CD_FUSED_CASES = [
+    ((523, 301), True, 9, 150),        # 2D: several warps per row, row length not a multiple of the vector width
+    ((260, 140), False, 7, 150),
+    ((140, 37, 150), True, 6, 70),     # 3D: two x tiles, partial y tile, three z chunks (zc = 64)
+    ((67, 30, 41), False, 5, 60),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,freetop,halo,nt", CD_FUSED_CASES)
+def test_cd_fused_multi_tile_forward_and_gradient(dtype, n, freetop, halo, nt):
+    case = acoustic_case(kind="acoustic_cd", n=n, nt=nt, halo=halo, freetop=freetop, dtype=dtype, seed=41 + len(n), nshots=2, nsrc=2, nrec=12)
+    rng = np.random.default_rng(7)
+    for s in case["shots"]:  # sources close enough to the receivers for the wave to arrive within nt steps; one inside a C-PML strip
+        s["src_positions"][:, -1] = rng.uniform(12, 22, size=2) * case["h"]
+        s["src_positions"][0, 0] = 3.0 * case["h"]
+        s["rec_positions"][0, 0] = (n[0] - 3) * case["h"]
+    ref, _ = oracle_forward(case)
+    got, _ = _forward_product(case, fused=True)
+    for r, g in zip(ref, got):
+        assert np.max(np.abs(r)) > 0
+        assert rel_l2(g, r) <= (1e-12 if dtype == np.float64 else 1e-6)
+    observed = make_observed(case, ref)
+    for cf in ((11, 1) if len(n) == 2 else (9,)):
+        (gref, mref), _, _ = oracle_gradient(case, observed, check_freq=cf, mute_src=3, mute_rec=1)
+        (ggot, mgot), _ = _gradient_product(case, observed, check_freq=cf, mute_src=3, mute_rec=1, fused=True)
+        for k in gref:
+            assert np.max(np.abs(gref[k])) > 0
+            assert rel_l2(ggot[k], gref[k]) <= (1e-11 if dtype == np.float64 else 2e-5), (k, cf)
+        assert abs(float(mgot) - float(mref)) <= tol(dtype) * abs(float(mref))
+
+
+@pytest.mark.parametrize("n", [(300, 170), (70, 45, 80)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cd_fused_equals_unfused_bitwise(n, dtype):
+    """the fused single-launch step and the one-launch-per-reference-kernel path perform the same operations"""
+    case = acoustic_case(kind="acoustic_cd", n=n, nt=90, halo=6, dtype=dtype, seed=8, nshots=1, nrec=16)
+    a, _ = _forward_product(case, fused=True)
+    b, _ = _forward_product(case, fused=False)
+    assert np.array_equal(a[0], b[0])
+    syn, _ = oracle_forward(case)
+    observed = make_observed(case, syn)
+    for cf in (1, 2, 3, 8):
+        (ga, ma), _ = _gradient_product(case, observed, check_freq=cf, fused=True)
+        (gb, mb), _ = _gradient_product(case, observed, check_freq=cf, fused=False)
+        assert np.array_equal(ga["vp"], gb["vp"]), cf
+        assert ma == mb
+
+
+def test_cd_fused_points_on_faces_and_fast_f32():
+    """sources / receivers on the grid faces (cells the stencil never updates) and the pure-Float32 arithmetic mode"""
+    case = acoustic_case(kind="acoustic_cd", n=(200, 120), nt=120, halo=8, dtype=np.float32, seed=9, nshots=1, nsrc=2, nrec=6)
+    h = case["h"]
+    case["shots"][0]["rec_positions"][0, :] = (0.0, 40 * h)           # i = 1 face
+    case["shots"][0]["rec_positions"][1, :] = (199 * h, 50 * h)       # i = nx face
+    case["shots"][0]["rec_positions"][2, :] = (100 * h, 0.0)          # j = 1 face
+    case["shots"][0]["src_positions"][1, :] = (60 * h, 0.0)           # a source on the top face
+    ref, _ = oracle_forward(case)
+    got, _ = _forward_product(case, fused=True)
+    assert rel_l2(got[0], ref[0]) <= 1e-6
+    fast, _ = _forward_product(case, fused=True, fast_f32=True)
+    assert rel_l2(fast[0], ref[0]) <= tol(np.float32)
+    observed = make_observed(case, ref)
+    (gref, _), _, _ = oracle_gradient(case, observed, check_freq=7)
+    (ggot, _), _ = _gradient_product(case, observed, check_freq=7, fused=True, fast_f32=True)
+    assert rel_l2(ggot["vp"], gref["vp"]) <= tol(np.float32)
