@@ -284,12 +284,64 @@ __device__ __forceinline__ CT cd_axis_term(const CT (&w1)[2], const CT (&w2)[3],
     return (D2 + dpsi) + (CT)xn;
 }
 
+// compact strip index of 1-based cell index c along an axis of extent n (0: not in a strip)
+__device__ __forceinline__ int strip_index(int c, int n, int h)
+{
+    if (c <= h)
+        return c;
+    if (c >= n - h + 1)
+        return c - (n - h) + 1 + h;
+    return 0;
+}
+
+// The same operator for the V cells of one vector along an axis whose memory-variable arrays have x fastest (y and z):
+// the cells share the strip index ii, so psi / xi move as 16-byte vectors (row pitch ld keeps them aligned).
+//   ok[v]: the cell is updated (interior in x); other cells keep their psi / xi
+template <class T, class CT, int V, bool FMA>
+__device__ __forceinline__ void cd_axis_term_vec(CT (&term)[V], const CT (&w1)[2], const CT (&w2)[3], const CT (&lo)[V], const CT (&mid)[V], const CT (&hi)[V],
+                                                 const bool (&ok)[V], int c1b, int n, int h, T inv, const T *__restrict__ a, const T *__restrict__ b,
+                                                 const T *__restrict__ a_h, const T *__restrict__ b_h, const T *__restrict__ psi_in, T *__restrict__ psi_out,
+                                                 T *__restrict__ xi, long long stride)
+{
+    const CT inv2 = (CT)(inv * inv);
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        term[v] = d2<CT, FMA>(w2, lo[v], mid[v], hi[v], inv2);
+    const int ii = strip_index(c1b, n, h);
+    if (ii == 0)
+        return;
+    typedef CVec<T, V> VT;
+    const VT ph = ldv<T, V>(psi_in + (long long)(ii - 1) * stride), pl = ldv<T, V>(psi_in + (long long)(ii - 2) * stride);
+    VT xo = ldv<T, V>(xi + (long long)(ii - 1) * stride);
+    const T ah1 = a_h[ii - 1], bh1 = b_h[ii - 1], ah0 = a_h[ii - 2], bh0 = b_h[ii - 2], a1 = a[ii - 1], b1 = b[ii - 1];
+    VT psi_hi = ph, psi_lo = pl;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        if (!ok[v])
+            continue;
+        const CT Dhi = (w1[0] * mid[v] + w1[1] * hi[v]) * (CT)inv;
+        const CT Dlo = (w1[0] * lo[v] + w1[1] * mid[v]) * (CT)inv;
+        (void)cpml_apply<T, CT>(Dhi, ah1, bh1, ph.v[v], psi_hi.v[v]);
+        (void)cpml_apply<T, CT>(Dlo, ah0, bh0, pl.v[v], psi_lo.v[v]);
+        const CT dpsi = (w1[0] * (CT)psi_lo.v[v] + w1[1] * (CT)psi_hi.v[v]) * (CT)inv;
+        const T bx = b1 * xo.v[v];
+        const T xn = (T)((CT)bx + (CT)a1 * (term[v] + dpsi));
+        xo.v[v] = xn;
+        term[v] = (term[v] + dpsi) + (CT)xn;
+    }
+    stv<T, V>(psi_out + (long long)(ii - 1) * stride, psi_hi);
+    if (c1b == 2 || c1b == n - h + 1) // the strip's first entry has no interior cell of its own
+        stv<T, V>(psi_out + (long long)(ii - 2) * stride, psi_lo);
+    stv<T, V>(xi + (long long)(ii - 1) * stride, xo);
+}
+
 template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
-__global__ void __launch_bounds__(CDF_RIM_T) cd_rim_kernel(const CdFusedParams<T> P)
+__global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? 8 : 4) cd_rim_kernel(const CdFusedParams<T> P)
 {
     constexpr int V = 16 / (int)sizeof(T);
     typedef CVec<T, V> VT;
-    const long long vid = (long long)blockIdx.x * CDF_RIM_T + threadIdx.x;
+    const int tid = (int)threadIdx.x, cta = (int)blockIdx.x;
+    const long long vid = (long long)blockIdx.x * CDF_RIM_T + tid;
     if (vid >= P.nrimvec)
         return;
     int bi = 0;
@@ -298,60 +350,93 @@ __global__ void __launch_bounds__(CDF_RIM_T) cd_rim_kernel(const CdFusedParams<T
         if (b < P.nbox && vid >= P.box[b].start)
             bi = b;
     const CdBox &B = P.box[bi];
-    const long long loc = vid - B.start;
-    const int iv = B.iv0 + (int)(loc % B.nvx);
-    const long long r = loc / B.nvx;
-    const int j = B.j0 + (int)(r % B.ny), k = B.k0 + (int)(r / B.ny);
+    const unsigned loc = (unsigned)(vid - B.start); // a box holds fewer than 2^31 vectors (checked on the host)
+    const unsigned r = loc / (unsigned)B.nvx, kk = r / (unsigned)B.ny;
+    const int iv = B.iv0 + (int)(loc - r * (unsigned)B.nvx);
+    const int j = B.j0 + (int)(r - kk * (unsigned)B.ny), k = B.k0 + (int)kk;
     const int i0 = iv * V;
     const int nx = P.nx, ny = P.ny, nz = P.nz, h = P.halo;
     const long long ld = P.ld, plane = P.plane;
     const long long off = (long long)k * plane + (long long)j * ld + i0;
 
     VT out = ldv<T, V>(P.pold + off); // faces (and pitch padding) keep pold
+    VT c2 = {}, c1 = {}, c0 = {}, g = {};
+    if (ADJ) {
+        c2 = ldv<T, V>(P.pm2 + off);
+        c1 = ldv<T, V>(P.pm1 + off);
+        c0 = ldv<T, V>(P.p0 + off);
+        g = ldv<T, V>(P.grad + off);
+    }
     const bool y_int = !HAS_Y || (j >= 1 && j <= ny - 2);
     const bool z_int = k >= 1 && k <= nz - 2;
     if (y_int && z_int) {
         const VT pcv = ldv<T, V>(P.pcur + off), fcv = ldv<T, V>(P.fact + off);
-        const VT zm = ldv<T, V>(P.pcur + off - plane), zp = ldv<T, V>(P.pcur + off + plane);
-        VT yu = {}, yd = {};
+        const VT zmv = ldv<T, V>(P.pcur + off - plane), zpv = ldv<T, V>(P.pcur + off + plane);
+        VT yuv = {}, ydv = {};
         if (HAS_Y) {
-            yu = ldv<T, V>(P.pcur + off - ld);
-            yd = ldv<T, V>(P.pcur + off + ld);
+            yuv = ldv<T, V>(P.pcur + off - ld);
+            ydv = ldv<T, V>(P.pcur + off + ld);
         }
         const T xl_in = i0 > 0 ? P.pcur[off - 1] : (T)0;
         const T xr_in = i0 + V < nx ? P.pcur[off + V] : (T)0;
         const CT w1[2] = {(CT)P.c1[0], (CT)P.c1[1]};
         const CT w2[3] = {(CT)P.c2[0], (CT)P.c2[1], (CT)P.c2[2]};
-        const long long jk = (long long)k * ny + j; // line index for the x-strip arrays
+        CT pc[V], lo[V], hi[V], tx[V], tyz[V];
+        bool ok[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            const int i = i0 + v;
-            if (i < 1 || i > nx - 2)
-                continue;
-            const CT pc = (CT)pcv.v[v];
+            pc[v] = (CT)pcv.v[v];
+            ok[v] = i0 + v >= 1 && i0 + v <= nx - 2;
+        }
+        // x term: plain everywhere, C-PML for the cells inside the x strips (psi_x / xi_x have the strip index fastest)
+        const CT i2x = (CT)(P.inv_d[0] * P.inv_d[0]);
+        const bool x_strip = h > 0 && (i0 + 1 <= h || i0 + V >= nx - h + 1);
+        const long long jk = (long long)k * ny + j;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
             const CT xl = (CT)(v > 0 ? pcv.v[v > 0 ? v - 1 : 0] : xl_in);
             const CT xr = (CT)(v < V - 1 ? pcv.v[v < V - 1 ? v + 1 : 0] : xr_in);
-            CT lap = cd_axis_term<T, CT, FMA>(w1, w2, xl, pc, xr, i + 1, nx, h, P.inv_d[0], P.a[0], P.b[0], P.a_h[0], P.b_h[0], P.psi_in[0] + jk * (2 * h),
-                                              P.psi_out[0] + jk * (2 * h), P.xi[0] + jk * (2 * (h + 1)), 1);
-            if (HAS_Y)
-                lap = lap + cd_axis_term<T, CT, FMA>(w1, w2, (CT)yu.v[v], pc, (CT)yd.v[v], j + 1, ny, h, P.inv_d[1], P.a[1], P.b[1], P.a_h[1], P.b_h[1],
-                                                     P.psi_in[1] + (long long)k * nx * (2 * h) + i, P.psi_out[1] + (long long)k * nx * (2 * h) + i,
-                                                     P.xi[1] + (long long)k * nx * (2 * (h + 1)) + i, nx);
-            lap = lap + cd_axis_term<T, CT, FMA>(w1, w2, (CT)zm.v[v], pc, (CT)zp.v[v], k + 1, nz, h, P.inv_d[2], P.a[2], P.b[2], P.a_h[2], P.b_h[2],
-                                                 P.psi_in[2] + (long long)j * nx + i, P.psi_out[2] + (long long)j * nx + i, P.xi[2] + (long long)j * nx + i,
-                                                 (long long)nx * ny);
-            out.v[v] = leapfrog<T, CT, FMA>(pc, out.v[v], fcv.v[v], lap);
+            if (x_strip && ok[v])
+                tx[v] = cd_axis_term<T, CT, FMA>(w1, w2, xl, pc[v], xr, i0 + v + 1, nx, h, P.inv_d[0], P.a[0], P.b[0], P.a_h[0], P.b_h[0],
+                                                 P.psi_in[0] + jk * (2 * h), P.psi_out[0] + jk * (2 * h), P.xi[0] + jk * (2 * (h + 1)), 1);
+            else
+                tx[v] = d2<CT, FMA>(w2, xl, pc[v], xr, i2x);
         }
+        if (HAS_Y) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                lo[v] = (CT)yuv.v[v];
+                hi[v] = (CT)ydv.v[v];
+            }
+            const long long o = (long long)k * ld * (2 * h) + i0, ox = (long long)k * ld * (2 * (h + 1)) + i0;
+            cd_axis_term_vec<T, CT, V, FMA>(tyz, w1, w2, lo, pc, hi, ok, j + 1, ny, h, P.inv_d[1], P.a[1], P.b[1], P.a_h[1], P.b_h[1], P.psi_in[1] + o,
+                                            P.psi_out[1] + o, P.xi[1] + ox, ld);
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                tx[v] = tx[v] + tyz[v];
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            lo[v] = (CT)zmv.v[v];
+            hi[v] = (CT)zpv.v[v];
+        }
+        {
+            const long long o = (long long)j * ld + i0;
+            cd_axis_term_vec<T, CT, V, FMA>(tyz, w1, w2, lo, pc, hi, ok, k + 1, nz, h, P.inv_d[2], P.a[2], P.b[2], P.a_h[2], P.b_h[2], P.psi_in[2] + o,
+                                            P.psi_out[2] + o, P.xi[2] + o, ld * ny);
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (ok[v])
+                out.v[v] = leapfrog<T, CT, FMA>(pc[v], out.v[v], fcv.v[v], tx[v] + tyz[v]);
     }
-    const int cta = (int)blockIdx.x, code0 = (int)threadIdx.x * V;
+    const int code0 = tid * V;
     if (P.inj_it > 0)
         inject_points<T, V>(P, P.inj[1], cta, code0, out);
     stv<T, V>(P.pnew + off, out);
     if (P.rec_it > 0)
         record_points<T, V>(P, P.rec[1], cta, code0, out);
     if (ADJ) {
-        const VT c2 = ldv<T, V>(P.pm2 + off), c1 = ldv<T, V>(P.pm1 + off), c0 = ldv<T, V>(P.p0 + off);
-        VT g = ldv<T, V>(P.grad + off);
 #pragma unroll
         for (int v = 0; v < V; ++v)
             g.v[v] = correlate<T, CT, FMA>(g.v[v], out.v[v], c2.v[v], c1.v[v], c0.v[v], P.inv_dt2);
@@ -394,6 +479,7 @@ CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool h
     auto add = [&](int iv0, int nvx, int j0, int nyb, int k0, int nzb) {
         if (nvx <= 0 || nyb <= 0 || nzb <= 0)
             return;
+        SWB_REQUIRE((long long)nvx * nyb * nzb < (1ll << 31), "grid too large for the fused CD rim enumeration");
         CdBox &b = g.box[g.nbox++];
         b.iv0 = iv0, b.j0 = j0, b.k0 = k0, b.nvx = nvx, b.ny = nyb, b.nz = nzb, b.start = start;
         start += (long long)nvx * nyb * nzb;

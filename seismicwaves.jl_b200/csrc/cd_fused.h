@@ -38,8 +38,9 @@ struct CdFusedParams {
     T inv_d[3];            // 1 / spacing along kernel axes x, y, z
     const T *pcur, *pold, *fact;
     T *pnew;               // may alias pold
-    // C-PML memory variables in the reference's dense layouts: psi_x (2h, ny, nz), psi_y (nx, 2h, nz), psi_z (nx, ny, 2h);
-    // xi_* likewise with 2(h+1).  psi is double-buffered (a cell needs the new psi of its lower neighbour, which that
+    // C-PML memory variables: psi_x (2h, ny, nz) as in the reference; psi_y (ld, 2h, nz) and psi_z (ld, ny, 2h) with the
+    // fields' row pitch so that a thread's V cells move as one aligned vector; xi_* likewise with 2(h+1).
+    // psi is double-buffered (a cell needs the new psi of its lower neighbour, which that
     // neighbour's thread computes too); xi is updated in place (one owner per entry).
     const T *psi_in[3];
     T *psi_out[3];
