@@ -1,0 +1,68 @@
+// ela_fused.h -- parameter blocks and layout constants of the fused 2D elastic P-SV step (ela_fused.cu).
+#pragma once
+#include "common.cuh"
+
+namespace swb {
+
+constexpr int ELF_TX = 128; // tile width in cells
+constexpr int ELF_TZ = 16;  // tile height in cells
+constexpr int ELF_GB = 5;   // zero guard rows in front of a padded plane (4 halo rows + the left halo of row -4)
+constexpr int ELF_GA = ELF_TZ + 8; // zero guard rows behind it
+
+// Padded plane: row pitch ld >= nx + 8 (multiple of 32 elements): at least 4 zero columns after the last cell of a row
+// and 4 before the first cell of the next one, so the 4-point stencils of a tile's halo read zeros outside every
+// array's index range -- the reference's derivative wrappers pad with zeros there
+// (src/models/elastic/backends/shared/freesurface_derivatives_4th_mirror.jl:72-244).
+inline long long elf_ld(long long nx) { return ((nx + 8 + 31) / 32) * 32; }
+inline size_t elf_plane_elems(long long nx, long long nz) { return (size_t)elf_ld(nx) * (size_t)(nz + ELF_GB + ELF_GA); }
+inline size_t elf_origin(long long nx) { return (size_t)elf_ld(nx) * ELF_GB; }
+
+template <class T>
+struct ElaFusedParams {
+    int nx, nz, halo, freetop;
+    long long ld;
+    T inv_dx, inv_dz, dt;
+    // padded planes, pointers to cell (1,1) of each array (ux: (nx-1, nz), uz: (nx, nz-1), ...)
+    const T *uxc, *uzc, *uxo, *uzo;
+    T *uxn, *uzn; // may alias uxo / uzo
+    const T *lam, *mu, *mu_hh, *rho_ih, *rho_jh;
+    // C-PML memory variables, dense reference layouts (ela_models.jl:275-299), double-buffered because a tile recomputes
+    // the stresses of its halo: 0 ψ_∂σxx∂x (2h, nz)  1 ψ_∂σxz∂x (2(h+1), nz-1)  2 ψ_∂σzz∂z (nx, 2h)  3 ψ_∂σxz∂z (nx-1, 2(h+1))
+    //                           4 ψ_∂ux∂x (2(h+1), nz)  5 ψ_∂uz∂x (2h, nz-1)  6 ψ_∂ux∂z (nx-1, 2h)  7 ψ_∂uz∂z (nx, 2(h+1))
+    const T *psi_in[8];
+    T *psi_out[8];
+    const T *a_x, *a_xh, *b_x, *b_xh, *a_z, *a_zh, *b_z, *b_zh;
+    // moment-tensor injection into the on-chip stresses: per-tile lists over the tile's stress region (tile + 2 halo cells),
+    // entries grouped by source in index order.  mt_it = 0 disables.
+    const int *mt_off, *mt_cell, *mt_src; // cell = field * region + offset inside the region; field 0: σxx and σzz, 1: σxz
+    const T *mt_coef;
+    const T *srctf, *Mxx, *Mzz, *Mxz;
+    long long nt;
+    int mt_it;
+};
+
+template <class T>
+void ela_fused_launch(const ElaFusedParams<T> &P, bool fast, cudaStream_t st);
+
+// region of on-chip stresses of a tile: rows -2 .. TZ+1, columns -2 .. TX+1
+constexpr int ELF_SW = ELF_TX + 4;
+constexpr int ELF_SREGION = (ELF_TZ + 4) * ELF_SW;
+
+// small kernels on the padded layout (sinc lists as uploaded by the engine: 1-based (i, j) into the array they address)
+// external-force / adjoint-source injection into unew (elastic2D_iso_xPU.jl:96-106), sources in index order
+void elf_inject_force(int dtype, long long ld, void *ux, void *uz, const void *rho_ih, const void *rho_jh, const swb_sinc_points &l0, const swb_sinc_points &l1,
+                      const void *tf, long long nt, long long it, double dt, cudaStream_t st);
+// traces[it, c, r] = sum_p coef[p] * u[ij[p]] (elastic2D_iso_xPU.jl:108-118, 219-230)
+void elf_record(int dtype, long long ld, const void *ux, const void *uz, const swb_sinc_points &lx, const swb_sinc_points &lz, void *traces, long long nt,
+                long long it, cudaStream_t st);
+// correlate_gradients! (elastic/backends/shared/correlate_gradient_xPU.jl:1-83) on padded planes
+struct ElaCorrPadded {
+    int dtype, flags, nx, nz, freetop;
+    long long ld;
+    double dx, dz, dt;
+    const void *aux, *auz, *uxo, *uzo, *uxc, *uzc, *uxn, *uzn, *lam, *mu;
+    void *g_ri, *g_rj, *g_l, *g_m, *g_mh;
+};
+void elf_correlate(const ElaCorrPadded &a, cudaStream_t st);
+
+} // namespace swb

@@ -5,13 +5,16 @@
 // ("ucur" with width 2 + the four ψ groups, ela_models.jl:383-396), the re-forwarding and the correlations run inside the
 // library on the sim's stream; the host sees seismograms, the adjoint source and the finished gradients only.
 #include "engine.h"
+#include "ela_fused.h"
 #include <cstring>
 
 namespace swb {
 
 class ElasticIso : public SimBase {
   public:
-    explicit ElasticIso(const swb_sim_desc &d) : SimBase(d)
+    // own_state = false: a subclass keeps the wavefield state in its own layout (fused engine below); the dense state is
+    // then allocated on demand only (snapshots run through this class's step-by-step path)
+    explicit ElasticIso(const swb_sim_desc &d, bool own_state = true) : SimBase(d)
     {
         SWB_REQUIRE(d.ndim == 2, "Only elastic 2D is currently implemented.");
         nx_ = d.n[0];
@@ -29,22 +32,28 @@ class ElasticIso : public SimBase {
         psib_[3][0] = esize * (nx_ - 1) * 2 * h, psib_[3][1] = esize * nx_ * 2 * (h + 1);
         rho_ = dalloc(nb_), lam_ = dalloc(nb_), mu_ = dalloc(nb_);
         rho_ih_ = dalloc(nbx_), rho_jh_ = dalloc(nbz_), mu_hh_ = dalloc(nbxz_);
-        alloc_state(fw_);
+        if (own_state) {
+            alloc_state(fw_);
+            fw_ready_ = true;
+        }
         if (d.gradient) {
-            alloc_state(ad_);
+            if (own_state)
+                alloc_state(ad_);
             g_ri_ = dalloc(nbx_), g_rj_ = dalloc(nbz_), g_l_ = dalloc(nb_), g_m_ = dalloc(nb_), g_mh_ = dalloc(nbxz_);
             for (int k = 0; k < 3; ++k) {
                 work_[k] = dalloc(nb_);
                 total_grad_.push_back(dalloc(nb_));
             }
-            std::vector<DeviceCheckpointer::FieldSpec> fs(5);
-            fs[0].comp_bytes = {nbx_, nbz_};
-            fs[0].width = 2;
-            fs[0].buffered = true; // "ucur"
-            for (int gq = 0; gq < 4; ++gq)
-                fs[1 + gq].comp_bytes = {psib_[gq][0], psib_[gq][1]};
-            ckpt_.reset(new DeviceCheckpointer(d.nt, d.check_freq, fs, stream));
-            dev_bytes_ += (int64_t)ckpt_->bytes();
+            if (own_state) {
+                std::vector<DeviceCheckpointer::FieldSpec> fs(5);
+                fs[0].comp_bytes = {nbx_, nbz_};
+                fs[0].width = 2;
+                fs[0].buffered = true; // "ucur"
+                for (int gq = 0; gq < 4; ++gq)
+                    fs[1 + gq].comp_bytes = {psib_[gq][0], psib_[gq][1]};
+                ckpt_.reset(new DeviceCheckpointer(d.nt, d.check_freq, fs, stream));
+                dev_bytes_ += (int64_t)ckpt_->bytes();
+            }
             misfit_acc_ = dalloc(sizeof(double));
         }
         sync();
@@ -105,7 +114,11 @@ class ElasticIso : public SimBase {
 
     void forward(void *host_seis, int snapevery) override
     {
-        begin_shot();
+        if (!fw_ready_) {
+            alloc_state(fw_);
+            fw_ready_ = true;
+        }
+        ElasticIso::begin_shot();
         snapshots_.clear();
         for (int64_t it = 1; it <= desc.nt; ++it) {
             step(fw_, false, it, true);
@@ -214,7 +227,7 @@ class ElasticIso : public SimBase {
         download(host_out, src, b);
     }
 
-  private:
+  protected:
     struct State { // one wavefield state (forward or adjoint): three displacement time levels, σ, eight ψ arrays
         DevBuf ubuf[3][2], sig[3], psi[4][2];
         void *u[3][2]; // rotating handles: [0] old, [1] cur, [2] new
@@ -284,14 +297,14 @@ class ElasticIso : public SimBase {
     }
 
     // reset! (ela_models.jl:436-442)
-    void begin_shot()
+    virtual void begin_shot()
     {
         use_device();
         SWB_REQUIRE(mat_set_, "material properties not set");
         SWB_REQUIRE(shot_bound_, "no shot bound");
         SWB_REQUIRE(cpml_set_[0] && cpml_set_[1], "C-PML coefficients not set for every axis");
         zero_state(fw_);
-        if (desc.gradient) {
+        if (desc.gradient && ckpt_) {
             zero_state(ad_);
             zero(g_ri_), zero(g_rj_), zero(g_l_), zero(g_m_), zero(g_mh_);
         }
@@ -366,7 +379,7 @@ class ElasticIso : public SimBase {
     }
 
     // ela_gradient.jl:93-154
-    void adjoint_loop()
+    virtual void adjoint_loop()
     {
         for (int64_t it = desc.nt; it >= 1; --it) {
             step(ad_, true, it, false);
@@ -429,9 +442,18 @@ class ElasticIso : public SimBase {
     DevBuf g_ri_, g_rj_, g_l_, g_m_, g_mh_, work_[3], misfit_acc_, obs_, mt_[3], mute_pos_[2];
     DevList src_l_[2], rec_l_[2];
     std::unique_ptr<DeviceCheckpointer> ckpt_;
-    bool mat_set_ = false;
+    bool mat_set_ = false, fw_ready_ = false;
 };
 
-SimBase *make_elastic_iso(const swb_sim_desc &d) { return new ElasticIso(d); }
+#include "engine_ela_fused.inc"
+
+SimBase *make_elastic_iso(const swb_sim_desc &d)
+{
+    // the fused engine (stresses on chip, one stencil launch per step) is the default; SWB_FLAG_NO_FUSION selects the
+    // one-launch-per-reference-kernel path
+    if (!(d.flags & SWB_FLAG_NO_FUSION) && d.n[0] >= 16 && d.n[1] >= 16)
+        return new ElasticIsoFused(d);
+    return new ElasticIso(d);
+}
 
 } // namespace swb

@@ -10,7 +10,7 @@ from elastic_cases import elastic_case, make_observed, oracle_forward, oracle_gr
 pytestmark = pytest.mark.gpu
 
 
-def product_inputs(case, observed=None, check_freq=1, mute_src=0, mute_rec=0, fast_f32=False, snapevery=None):
+def product_inputs(case, observed=None, check_freq=1, mute_src=0, mute_rec=0, fast_f32=False, snapevery=None, fused=True):
     import swb200 as S
 
     T = case["dtype"].type
@@ -27,7 +27,7 @@ def product_inputs(case, observed=None, check_freq=1, mute_src=0, mute_rec=0, fa
         else:
             srcs = S.ExternalForceSources(s["src_positions"].astype(T), s["src_tf"].astype(T), T(s["domfreq"]))
             shots.append(S.ExternalForceShot(srcs=srcs, recs=recs))
-    runparams = S.RunParameters(parall="B200", fast_f32=fast_f32, snapevery=snapevery, erroronPPW=False)
+    runparams = S.RunParameters(parall="B200", fast_f32=fast_f32, fused=fused, snapevery=snapevery, erroronPPW=False)
     gradparams = S.GradParameters(mute_radius_src=mute_src, mute_radius_rec=mute_rec, compute_misfit=True, check_freq=check_freq)
     misfit = [S.L2Misfit(observed=o) for o in observed] if observed is not None else None
     return params, matprop, shots, misfit, runparams, gradparams
@@ -35,12 +35,13 @@ def product_inputs(case, observed=None, check_freq=1, mute_src=0, mute_rec=0, fa
 
 @pytest.mark.parametrize("kind", ["momten", "extforce"])
 @pytest.mark.parametrize("dtype,freetop,n", [(np.float64, True, (96, 80)), (np.float64, False, (83, 71)), (np.float32, True, (90, 77))])
-def test_forward_seismograms_match_oracle(kind, dtype, freetop, n):
+@pytest.mark.parametrize("fused", [False, True])
+def test_forward_seismograms_match_oracle(kind, dtype, freetop, n, fused):
     import swb200 as S
 
     case = elastic_case(n=n, nt=150, halo=7, freetop=freetop, dtype=dtype, kind=kind, nshots=2, nsrc=2, nrec=5, seed=13)
     ref, _ = oracle_forward(case)
-    params, matprop, shots, _, runparams, _ = product_inputs(case)
+    params, matprop, shots, _, runparams, _ = product_inputs(case, fused=fused)
     S.swforward(params, matprop, shots, runparams=runparams)
     for r, sh in zip(ref, shots):
         g = sh.recs.seismograms
@@ -52,14 +53,15 @@ def test_forward_seismograms_match_oracle(kind, dtype, freetop, n):
 
 @pytest.mark.parametrize("kind,dtype,check_freq", [("momten", np.float64, 1), ("momten", np.float64, 7), ("extforce", np.float64, 10), ("extforce", np.float32, 9),
                                                    ("momten", np.float32, 1)])
-def test_gradient_and_misfit_match_oracle(kind, dtype, check_freq):
+@pytest.mark.parametrize("fused", [False, True])
+def test_gradient_and_misfit_match_oracle(kind, dtype, check_freq, fused):
     import swb200 as S
 
     case = elastic_case(n=(72, 64), nt=100, halo=6, dtype=dtype, kind=kind, nshots=2, nrec=4, seed=17 + check_freq)
     syn, _ = oracle_forward(case)
     obs = make_observed(case, syn)
     (gref, mref), sref = oracle_gradient(case, obs, check_freq=check_freq, mute_src=3, mute_rec=1)
-    params, matprop, shots, misfit, runparams, gradparams = product_inputs(case, observed=obs, check_freq=check_freq, mute_src=3, mute_rec=1)
+    params, matprop, shots, misfit, runparams, gradparams = product_inputs(case, observed=obs, check_freq=check_freq, mute_src=3, mute_rec=1, fused=fused)
     ggot, mgot = S.swgradient(params, matprop, shots, misfit, runparams=runparams, gradparams=gradparams)
     assert set(ggot) == {"rho", "lambda", "mu"}
     for k in gref:
@@ -118,3 +120,61 @@ def test_nearest_grid_point_sources_and_snapshots():
             assert rel_l2(snaps[0][it]["ucur"][c], snaps_ref[0][it]["ucur"][c]) <= 1e-12
         for c in range(3):
             assert rel_l2(snaps[0][it]["σ"][c], snaps_ref[0][it]["sigma"][c]) <= 1e-12
+
+
+# ---- fused engine (stresses on chip) on grids that span many tiles: interior fast-path tiles + C-PML / edge / free-surface tiles ----
+
+
+@pytest.mark.parametrize("kind", ["momten", "extforce"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,freetop", [((420, 150), True), ((301, 97), False)])
+def test_fused_multi_tile_forward_and_gradient(kind, dtype, n, freetop):
+    import swb200 as S
+
+    case = elastic_case(n=n, nt=130, halo=9, freetop=freetop, dtype=dtype, kind=kind, nshots=1, nsrc=2, nrec=6, seed=23)
+    for s in case["shots"]:  # a source close to the receivers so that the wave arrives within nt steps
+        s["src_positions"][:, 1] = np.array([14.3, 19.8])[: s["src_positions"].shape[0]] * case["h"]
+    ref, _ = oracle_forward(case)
+    params, matprop, shots, _, runparams, _ = product_inputs(case, fused=True)
+    S.swforward(params, matprop, shots, runparams=runparams)
+    for r, sh in zip(ref, shots):
+        assert np.max(np.abs(r)) > 0
+        assert rel_l2(sh.recs.seismograms, r) <= (1e-12 if dtype == np.float64 else 2e-6)
+    obs = make_observed(case, ref)
+    for cf in (11, 1):
+        (gref, mref), _ = oracle_gradient(case, obs, check_freq=cf, mute_src=3, mute_rec=1)
+        params, matprop, shots, misfit, runparams, gradparams = product_inputs(case, observed=obs, check_freq=cf, mute_src=3, mute_rec=1, fused=True)
+        ggot, mgot = S.swgradient(params, matprop, shots, misfit, runparams=runparams, gradparams=gradparams)
+        for k in gref:
+            assert np.max(np.abs(gref[k])) > 0
+            assert rel_l2(ggot[k], gref[k]) <= (1e-10 if dtype == np.float64 else 5e-5), (k, cf)
+        assert abs(float(mgot) - float(mref)) <= tol(dtype) * abs(float(mref))
+
+
+@pytest.mark.parametrize("kind", ["momten", "extforce"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fused_equals_unfused_bitwise(kind, dtype):
+    """the fused step (stresses on chip, halo recomputed) performs the operations of the four-sweep path"""
+    import swb200 as S
+
+    case = elastic_case(n=(300, 140), nt=100, halo=8, dtype=dtype, kind=kind, nshots=1, nsrc=2, nrec=5, seed=29)
+    for s in case["shots"]:
+        s["src_positions"][:, 1] = np.array([15.2, 21.7])[: s["src_positions"].shape[0]] * case["h"]
+    out = {}
+    for fused in (True, False):
+        params, matprop, shots, _, runparams, _ = product_inputs(case, fused=fused)
+        S.swforward(params, matprop, shots, runparams=runparams)
+        out[fused] = shots[0].recs.seismograms.copy()
+    assert np.max(np.abs(out[True])) > 0
+    assert np.array_equal(out[True], out[False])
+    obs = make_observed(case, [out[True]])
+    grads = {}
+    for fused in (True, False):
+        for cf in (1, 2, 3, 9):
+            params, matprop, shots, misfit, runparams, gradparams = product_inputs(case, observed=obs, check_freq=cf, fused=fused)
+            grads[(fused, cf)] = S.swgradient(params, matprop, shots, misfit, runparams=runparams, gradparams=gradparams)
+    for cf in (1, 2, 3, 9):
+        (ga, ma), (gb, mb) = grads[(True, cf)], grads[(False, cf)]
+        for k in ga:
+            assert np.array_equal(ga[k], gb[k]), (k, cf)
+        assert ma == mb

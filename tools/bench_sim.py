@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--kind", default="cd", choices=["cd", "vd"])
+    ap.add_argument("--kind", default="cd", choices=["cd", "vd", "ela"])
     ap.add_argument("--n", type=int, nargs="+", default=[768, 768, 768])
     ap.add_argument("--nt", type=int, default=40)
     ap.add_argument("--check-freq", type=int, default=10)
@@ -46,15 +46,22 @@ def main():
     vp = (1500.0 + 3000.0 * depth.reshape((1,) * (N - 1) + (n[-1],)) + np.zeros(n)).astype(T)
     vp += rng.normal(0, 30.0, size=n).astype(T)
     vp = np.asfortranarray(vp)
-    cfl = (6.0 / 7.0 if args.kind == "vd" else 1.0)
+    cfl = (6.0 / 7.0 if args.kind in ("vd", "ela") else 1.0)
     dt = 0.99 * cfl * h / (float(vp.max()) * math.sqrt(N))
     nt = args.nt
     bc = S.CPMLBoundaryConditionParameters(halo=args.halo, rcoef=T(1e-4), freeboundtop=True)
-    params = S.InputParametersAcoustic(nt, T(dt), n, tuple(T(h) for _ in n), bc, dtype=np.dtype(T))
+    PC = S.InputParametersElastic if args.kind == "ela" else S.InputParametersAcoustic
+    params = PC(nt, T(dt), n, tuple(T(h) for _ in n), bc, dtype=np.dtype(T))
     rp = S.RunParameters(parall="B200", erroronPPW=False, fast_f32=bool(args.fast_f32), fused=bool(args.fused))
     gp = S.GradParameters(mute_radius_src=2, mute_radius_rec=0, compute_misfit=True, check_freq=args.check_freq)
     if args.kind == "cd":
         matprop = S.VpAcousticCDMaterialProperties(vp)
+    elif args.kind == "ela":
+        vp64 = vp.astype(np.float64)
+        rho = np.full(n, 2100.0)
+        mu = (vp64 / np.sqrt(3.0)) ** 2 * rho
+        lam = vp64**2 * rho - 2 * mu
+        matprop = S.ElasticIsoMaterialProperties(np.asfortranarray(rho.astype(T)), np.asfortranarray(lam.astype(T)), np.asfortranarray(mu.astype(T)))
     else:
         matprop = S.VpRhoAcousticVDMaterialProperties(vp, np.asfortranarray((310.0 * vp.astype(np.float64) ** 0.25).astype(T)))
     f0 = 8.0
@@ -68,6 +75,10 @@ def main():
     rpos[:, -1] = 3 * h
 
     def shot():
+        if args.kind == "ela":
+            spo = sp + T(0.124)  # off-grid: exercises the sinc spreading
+            srcs = S.MomentTensorSources(spo, (tf * T(1e-3)).astype(T), [S.MomentTensor2D(T(5e10), T(5e10), T(0.89e10))], T(f0))
+            return S.MomentTensorShot(srcs=srcs, recs=S.VectorReceivers((rpos - T(0.324)).astype(T), nt, dtype=np.dtype(T)))
         return S.ScalarShot(srcs=S.ScalarSources(sp, tf, T(f0)), recs=S.ScalarReceivers(rpos, nt, dtype=np.dtype(T)))
 
     grad = not args.no_grad
@@ -76,9 +87,9 @@ def main():
     out = {"kind": args.kind, "n": list(n), "nt": nt, "check_freq": args.check_freq, "dtype": args.dtype, "fast_f32": args.fast_f32, "fused": args.fused,
            "device_GB": ws.device_bytes() / 1e9}
     es = np.dtype(T).itemsize
-    bytes_fwd = {"cd": 4, "vd": 9}[args.kind] * es
-    bytes_adj = {"cd": 9, "vd": 17}[args.kind] * es
-    obs = np.zeros((nt, args.nrec), dtype=T, order="F")
+    bytes_fwd = {"cd": 4, "vd": 9, "ela": 11}[args.kind] * es
+    bytes_adj = {"cd": 9, "vd": 17, "ela": 27}[args.kind] * es
+    obs = np.zeros((nt, 2, args.nrec) if args.kind == "ela" else (nt, args.nrec), dtype=T, order="F")
     for rep in range(args.reps + 1):
         if rep == 1:
             ws.kernel_timing(1)

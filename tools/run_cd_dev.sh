@@ -1,8 +1,8 @@
-B="python tools/bench_sim.py --kind cd"
+python -m pytest tests/test_gpu_elastic.py -m gpu -q -x -p no:logging 2>&1 | grep -v "points per wavelength\|instead of\|Grid spacing" | tail -30 > gpurun_out/ela_tests3.log
+B="python tools/bench_sim.py"
 {
-echo "3d768 fwd"; $B --n 768 768 768 --nt 30 --no-grad 2>/dev/null | tail -1
-echo "2d4096 grad"; $B --n 4096 4096 --nt 200 --check-freq 14 2>/dev/null | tail -1
-echo "C4 full: 3d768 grad nt500 cf50"; $B --n 768 768 768 --nt 500 --check-freq 50 --reps 1 --nrec 1024 2>&1 | tail -2
-nvidia-smi --query-gpu=memory.used,memory.total --format=csv
-} > gpurun_out/cd_bench8.log 2>&1
-python -m pytest tests/test_gpu_acoustic.py -m gpu -q -x -p no:logging -k "cd_fused" 2>&1 | tail -3 > gpurun_out/cd_tests8.log
+echo "ela 4096x2048 grad f32 fast"; $B --kind ela --n 4096 2048 --nt 100 --check-freq 10 --nrec 10 2>&1 | tail -1
+echo "ela 4096x2048 grad f32 faithful"; $B --kind ela --n 4096 2048 --nt 100 --check-freq 10 --nrec 10 --fast-f32 0 2>&1 | tail -1
+echo "ela 4096x2048 grad f64"; $B --kind ela --n 4096 2048 --nt 100 --check-freq 10 --nrec 10 --dtype f64 2>&1 | tail -1
+} > gpurun_out/ela_bench3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ela_fused -s 20 -c 1 -o gpurun_out/ela_fused_v2 $B --kind ela --n 4096 2048 --nt 40 --no-grad --nrec 10 --reps 0 > gpurun_out/ncu_ela_v2.log 2>&1
