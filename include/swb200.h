@@ -316,6 +316,14 @@ int32_t swb_comm_destroy(swb_comm *comm);
 int32_t swb_comm_allreduce_sum(swb_comm *comm, void *dev_ptr, size_t nelem, int32_t dtype, void *stream);
 int32_t swb_sim_allreduce_total_gradient(swb_sim *sim, swb_comm *comm);
 
+/* z-slab domain decomposition of a 3D acoustic constant-density FORWARD simulation too large for one GPU (BASELINE
+ * config 5; the reference has no counterpart).  The last axis is cut into contiguous slabs, one per rank.  Each rank creates
+ * an ordinary SWB_ACOU_CD sim whose n[2] counts its owned planes plus one ghost plane per interior face, and then declares
+ * the faces: lower_rank / upper_rank = the neighbour owning the planes below k = 1 / above k = n[2], or -1 at a true domain end
+ * (C-PML strip, Dirichlet face).  After every time step the first / last owned plane is sent to the neighbour's ghost plane
+ * with NCCL point-to-point transfers on the sim's stream.  Call before swb_sim_bind_scalar_shot; positions are slab-local. */
+int32_t swb_sim_set_slab(swb_sim *sim, swb_comm *comm, int32_t lower_rank, int32_t upper_rank);
+
 #ifdef __cplusplus
 }
 #endif

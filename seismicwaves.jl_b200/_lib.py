@@ -113,7 +113,7 @@ EXPORTS = [
     "swb_sim_gradient_forward", "swb_sim_gradient_adjoint", "swb_sim_gradient_l2", "swb_sim_get_raw_gradient",
     "swb_sim_accumulate_gradient", "swb_sim_zero_total_gradient", "swb_sim_total_gradient_ptr", "swb_sim_get_total_gradient",
     "swb_sim_cell_updates", "swb_sim_get_field", "swb_sim_stream", "swb_sim_kernel_timing", "swb_sim_kernel_timing_class",
-    "swb_comm_unique_id", "swb_comm_create", "swb_comm_destroy", "swb_comm_allreduce_sum", "swb_sim_allreduce_total_gradient",
+    "swb_comm_unique_id", "swb_comm_create", "swb_comm_destroy", "swb_comm_allreduce_sum", "swb_sim_allreduce_total_gradient", "swb_sim_set_slab",
 ]
 
 _lib = None
@@ -185,6 +185,7 @@ def load() -> C.CDLL:
         "swb_comm_destroy": [vp],
         "swb_comm_allreduce_sum": [vp, vp, sz, i32, vp],
         "swb_sim_allreduce_total_gradient": [vp, vp],
+        "swb_sim_set_slab": [vp, vp, i32, i32],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)

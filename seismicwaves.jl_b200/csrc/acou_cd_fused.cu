@@ -301,14 +301,14 @@ template <class T, class CT, int V, bool FMA>
 __device__ __forceinline__ void cd_axis_term_vec(CT (&term)[V], const CT (&w1)[2], const CT (&w2)[3], const CT (&lo)[V], const CT (&mid)[V], const CT (&hi)[V],
                                                  const bool (&ok)[V], int c1b, int n, int h, T inv, const T *__restrict__ a, const T *__restrict__ b,
                                                  const T *__restrict__ a_h, const T *__restrict__ b_h, const T *__restrict__ psi_in, T *__restrict__ psi_out,
-                                                 T *__restrict__ xi, long long stride)
+                                                 T *__restrict__ xi, long long stride, bool lo_on = true, bool hi_on = true)
 {
     const CT inv2 = (CT)(inv * inv);
 #pragma unroll
     for (int v = 0; v < V; ++v)
         term[v] = d2<CT, FMA>(w2, lo[v], mid[v], hi[v], inv2);
     const int ii = strip_index(c1b, n, h);
-    if (ii == 0)
+    if (ii == 0 || (ii <= h ? !lo_on : !hi_on)) // a slab-interior end of the axis has no strip
         return;
     typedef CVec<T, V> VT;
     const VT ph = ldv<T, V>(psi_in + (long long)(ii - 1) * stride), pl = ldv<T, V>(psi_in + (long long)(ii - 2) * stride);
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? 8 : 4) cd_rim_ker
         {
             const long long o = (long long)j * ld + i0;
             cd_axis_term_vec<T, CT, V, FMA>(tyz, w1, w2, lo, pc, hi, ok, k + 1, nz, h, P.inv_d[2], P.a[2], P.b[2], P.a_h[2], P.b_h[2], P.psi_in[2] + o,
-                                            P.psi_out[2] + o, P.xi[2] + o, ld * ny);
+                                            P.psi_out[2] + o, P.xi[2] + o, ld * ny, P.zpml_lo != 0, P.zpml_hi != 0);
         }
 #pragma unroll
         for (int v = 0; v < V; ++v)
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? 8 : 4) cd_rim_ker
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
-CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool has_y, int zc)
+CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool has_y, int zc, bool zpml_lo, bool zpml_hi)
 {
     CdFusedGeom g{};
     g.v = cdf_vec(esize);
@@ -464,8 +464,9 @@ CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool h
     g.ivhi = std::max(g.ivlo, (nx - g.hs) / g.v);
     g.jlo = has_y ? g.hs : 0;
     g.jhi = has_y ? std::max(g.jlo, ny - g.hs) : 1;
-    g.klo = g.hs;
-    g.khi = std::max(g.klo, nz - g.hs);
+    g.zpml_lo = zpml_lo, g.zpml_hi = zpml_hi;
+    g.klo = zpml_lo ? g.hs : 1;
+    g.khi = std::max(g.klo, nz - (zpml_hi ? g.hs : 1));
     g.ntx = (nx + g.tx - 1) / g.tx;
     g.nty = has_y ? (g.jhi - g.jlo + CDF_TY - 1) / CDF_TY : 1;
     g.ntz = (g.khi - g.klo + zc - 1) / zc;
@@ -534,6 +535,7 @@ int cd_fused_locate(const CdFusedGeom &g, int i, int j, int k, int *cta, int *co
 template <class T>
 void cd_fused_fill_geom(CdFusedParams<T> &P, const CdFusedGeom &g)
 {
+    P.zpml_lo = g.zpml_lo ? 1 : 0, P.zpml_hi = g.zpml_hi ? 1 : 0;
     P.jlo = g.jlo, P.jhi = g.jhi, P.klo = g.klo, P.khi = g.khi, P.ivlo = g.ivlo, P.ivhi = g.ivhi, P.zc = g.zc;
     P.nbox = g.nbox;
     for (int b = 0; b < g.nbox; ++b)

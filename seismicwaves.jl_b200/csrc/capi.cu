@@ -323,6 +323,10 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi &nccl()
@@ -337,6 +341,10 @@ NcclApi &nccl()
             a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
             a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
             a.AllReduce = (decltype(a.AllReduce))dlsym(a.h, "ncclAllReduce");
+            a.Send = (decltype(a.Send))dlsym(a.h, "ncclSend");
+            a.Recv = (decltype(a.Recv))dlsym(a.h, "ncclRecv");
+            a.GroupStart = (decltype(a.GroupStart))dlsym(a.h, "ncclGroupStart");
+            a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.h, "ncclGroupEnd");
             a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
         }
         return a;
@@ -351,6 +359,30 @@ void nccl_check(ncclResult_t r, const char *what)
         throw Error(SWB_ERR_NCCL, std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r) : "NCCL error"));
 }
 } // namespace
+
+} // extern "C"
+
+// halo exchange of a z-slab decomposition: one plane to / from each neighbour, all four transfers in one NCCL group
+void swb::comm_halo_exchange(swb_comm *comm, const void *send_lo, void *recv_lo, int lower, const void *send_hi, void *recv_hi, int upper, size_t nelem, int dtype,
+                             cudaStream_t st)
+{
+    SWB_REQUIRE(comm != nullptr && comm->comm != nullptr, "null communicator");
+    NcclApi &a = nccl();
+    SWB_REQUIRE(a.Send && a.Recv && a.GroupStart && a.GroupEnd, "this NCCL build has no point-to-point support");
+    const ncclDataType_t t = dtype == SWB_F64 ? ncclDouble : ncclFloat;
+    nccl_check(a.GroupStart(), "ncclGroupStart");
+    if (lower >= 0) {
+        nccl_check(a.Send(send_lo, nelem, t, lower, comm->comm, st), "ncclSend");
+        nccl_check(a.Recv(recv_lo, nelem, t, lower, comm->comm, st), "ncclRecv");
+    }
+    if (upper >= 0) {
+        nccl_check(a.Send(send_hi, nelem, t, upper, comm->comm, st), "ncclSend");
+        nccl_check(a.Recv(recv_hi, nelem, t, upper, comm->comm, st), "ncclRecv");
+    }
+    nccl_check(a.GroupEnd(), "ncclGroupEnd");
+}
+
+extern "C" {
 
 int32_t swb_comm_unique_id(void *id128)
 {
@@ -418,6 +450,20 @@ int32_t swb_sim_allreduce_total_gradient(swb_sim *sim, swb_comm *comm)
                    "ncclAllReduce");
     }
     SWB_CUDA(cudaStreamSynchronize(sim->impl->stream));
+    SWB_API_END
+}
+
+int32_t swb_sim_set_slab(swb_sim *sim, swb_comm *comm, int32_t lower_rank, int32_t upper_rank)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE(sim != nullptr && sim->impl, "null simulation handle");
+    SWB_REQUIRE(comm != nullptr || (lower_rank < 0 && upper_rank < 0), "a communicator is required when the slab has neighbours");
+    if (comm) {
+        SWB_REQUIRE(lower_rank < comm->nranks && upper_rank < comm->nranks && lower_rank != comm->rank && upper_rank != comm->rank, "bad neighbour rank");
+        SWB_REQUIRE(comm->device == sim->impl->desc.device, "communicator and simulation live on different devices");
+    }
+    sim->impl->use_device();
+    sim->impl->set_slab(comm, lower_rank, upper_rank);
     SWB_API_END
 }
 

@@ -34,6 +34,7 @@ struct CdPointList {
 template <class T>
 struct CdFusedParams {
     int nx, ny, nz, halo;
+    int zpml_lo, zpml_hi;  // 0: that z end is an interior face of a z-slab decomposition (one ghost plane, no C-PML strip)
     long long ld, plane;   // row pitch and plane pitch (elements) of pcur / pold / pnew / fact / grad / stored fields
     T inv_d[3];            // 1 / spacing along kernel axes x, y, z
     const T *pcur, *pold, *fact;
@@ -71,6 +72,7 @@ struct CdFusedGeom {
     int v, tx, ty, ntx, nty, ntz, zc;
     bool has_y;
     int nx, ny, nz, hs;                 // hs = max(halo, 1): thickness of the rim along each axis
+    bool zpml_lo, zpml_hi;              // false: slab-interior z end (rim = the ghost plane only)
     int jlo, jhi, klo, khi, ivlo, ivhi; // bulk ranges
     unsigned gx, gy, gz;                // bulk launch grid (0 blocks if the bulk is empty)
     int nbox;
@@ -79,7 +81,7 @@ struct CdFusedGeom {
     int ncta_bulk() const { return (int)(gx * gy * gz); }
     int ncta_rim() const { return (int)((nrimvec + CDF_RIM_T - 1) / CDF_RIM_T); }
 };
-CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool has_y, int zc);
+CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool has_y, int zc, bool zpml_lo = true, bool zpml_hi = true);
 // which kernel owns the 0-based cell (i, j, k): returns 0 (bulk) or 1 (rim), the CTA index in launch order and the packed in-CTA cell code
 int cd_fused_locate(const CdFusedGeom &g, int i, int j, int k, int *cta, int *code);
 template <class T>

@@ -119,6 +119,9 @@ class SimBase {
     virtual void accumulate_gradient(int64_t nsrcpos, const void *srcpos, int rs, int64_t nrecpos, const void *recpos, int rr) = 0;
     virtual int n_total_gradients() const = 0;
     virtual void get_field(const std::string &name, void *host_out, size_t nbytes) = 0;
+    // z-slab domain decomposition (forward only): this sim holds one slab of the last axis, ghost planes included; a negative
+    // neighbour rank marks a true domain end
+    virtual void set_slab(swb_comm *, int, int) { throw Error(SWB_ERR_ARG, "z-slab decomposition is available for the fused 3D acoustic constant-density engine only"); }
     void zero_total_gradient();
     void total_gradient_ptr(int which, void **p, size_t *nelem);
     void get_total_gradient(int which, void *host_out);
@@ -217,6 +220,10 @@ void SimBase::run_graph(Graph &g, F &&enqueue)
     cell_updates += g.updates;
     g_launches.fetch_add(g.launches);
 }
+
+// capi.cu (NCCL is resolved there)
+void comm_halo_exchange(swb_comm *comm, const void *send_lo, void *recv_lo, int lower, const void *send_hi, void *recv_hi, int upper, size_t nelem, int dtype,
+                        cudaStream_t st);
 
 SimBase *make_acoustic_cd(const swb_sim_desc &d);
 SimBase *make_acoustic_vd(const swb_sim_desc &d);

@@ -51,6 +51,16 @@ class ShotParallel:
         self.dist.all_reduce(m, op=self.dist.ReduceOp.SUM)
         return out, float(m.item())
 
+    def allreduce_max(self, value: float) -> float:
+        import torch
+
+        if self.world == 1:
+            return value
+        t = torch.tensor([value], dtype=torch.float64)
+        t = t.cuda(self.device) if self.dist.get_backend() == "nccl" else t
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- device-side reduction of the engine's total gradient (NCCL through libswb200) ---------------------------
     def _ensure_comm(self):
         import torch
@@ -94,3 +104,102 @@ def swgradient_sharded(wavesim, matprop, shots: Sequence, misfit: Sequence, sp: 
         _, tot = sp.allreduce_host({}, float(local_misfit))
         return grad, wavesim.T(tot)
     return grad
+
+
+# ---------------------------------------------------------------------------------------------------------
+# z-slab domain decomposition of one 3D acoustic constant-density forward simulation (BASELINE config 5)
+# ---------------------------------------------------------------------------------------------------------
+def slab_range(nz: int, world_size: int, rank: int) -> range:
+    """owned planes (0-based, along the last axis) of rank `rank`: contiguous, the first nz % world_size ranks own one more"""
+    base, rem = divmod(nz, world_size)
+    k0 = rank * base + min(rank, rem)
+    return range(k0, k0 + base + (1 if rank < rem else 0))
+
+
+def slab_local_planes(nz: int, world_size: int, rank: int) -> range:
+    """planes a rank stores: its owned ones plus one ghost plane per interior face"""
+    own = slab_range(nz, world_size, rank)
+    return range(own.start - (1 if rank > 0 else 0), own.stop + (1 if rank < world_size - 1 else 0))
+
+
+def slab_route_points(idx0: np.ndarray, nz: int, world_size: int, rank: int) -> np.ndarray:
+    """indices (into the point list) of the points whose 0-based plane idx0[:, -1] this rank owns"""
+    own = slab_range(nz, world_size, rank)
+    k = idx0[:, -1]
+    return np.nonzero((k >= own.start) & (k < own.stop))[0]
+
+
+class SlabForward3D:
+    """swforward! of ONE 3D acoustic CD shot on a grid cut into z slabs, one per rank (forward only).
+
+    Every rank passes the global parameters and only ITS slab of the velocity model (`vp_local`, planes
+    slab_local_planes(...), ghost planes included).  Sources / receivers are given with global positions; each is
+    bound on the rank that owns its plane (the others use a muted dummy so that the engine's shot contract holds),
+    and the seismograms are summed over the ranks at the end (every trace is non-zero on exactly one rank).
+    The local sims exchange one plane per interior face and time step over NCCL (swb_sim_set_slab)."""
+
+    def __init__(self, params, vp_local: np.ndarray, sp: "ShotParallel", runparams=None, vp_max_global: Optional[float] = None):
+        from . import api
+        from .types import InputParametersAcoustic, RunParameters, VpAcousticCDMaterialProperties
+
+        assert len(params.gridsize) == 3, "z-slab decomposition is for 3D grids"
+        self.sp, self.params = sp, params
+        self.nz = params.gridsize[2]
+        self.loc = slab_local_planes(self.nz, sp.world, sp.rank)
+        self.own = slab_range(self.nz, sp.world, sp.rank)
+        assert vp_local.shape == (params.gridsize[0], params.gridsize[1], len(self.loc)), "vp_local must hold this rank's planes (ghost planes included)"
+        T = params.dtype.type
+        lp = InputParametersAcoustic(params.ntimesteps, params.dt, (params.gridsize[0], params.gridsize[1], len(self.loc)), params.gridspacing, params.boundcond,
+                                     dtype=params.dtype)
+        rp = runparams or RunParameters(parall="B200", device=sp.device or 0)
+        matprop = VpAcousticCDMaterialProperties(np.asfortranarray(vp_local))
+        self.sim = api.build_wavesim(lp, matprop, runparams=rp)
+        self.sim.set_wavesim_matprop(matprop)
+        vmax = float(np.max(vp_local)) if vp_max_global is None else float(vp_max_global)
+        if vp_max_global is None and sp.world > 1:
+            vmax = sp.allreduce_max(vmax)
+        self.sim._vp_max = T(vmax)  # the C-PML profiles depend on the global maximum velocity (acou_init_bc.jl:13-17)
+        lower, upper = (sp.rank - 1 if sp.rank > 0 else -1), (sp.rank + 1 if sp.rank < sp.world - 1 else -1)
+        if sp.world > 1:
+            sp._ensure_comm()
+        _lib.check(_lib.load().swb_sim_set_slab(self.sim._h, sp._comm, lower, upper))
+        self.T = T
+
+    def forward(self, shot) -> np.ndarray:
+        """runs the shot and returns the full seismogram matrix (nt, nrec) on every rank"""
+        from . import hostprep
+        from .types import ScalarReceivers, ScalarShot, ScalarSources
+
+        T, sim, sp = self.T, self.sim, self.sp
+        spacing = self.params.gridspacing
+        nt = self.params.ntimesteps
+        gsrc = hostprep.find_nearest_grid_points(shot.srcs.positions, spacing, T) - 1  # 0-based global indices
+        grec = hostprep.find_nearest_grid_points(shot.recs.positions, spacing, T) - 1
+        isrc = slab_route_points(gsrc, self.nz, sp.world, sp.rank)
+        irec = slab_route_points(grec, self.nz, sp.world, sp.rank)
+        koff = self.loc.start
+
+        def local_positions(gidx, sel):
+            if len(sel) == 0:  # dummy point in the middle of the first owned plane (source: zero wavelet; receiver: trace discarded)
+                g = np.array([[self.params.gridsize[0] // 2, self.params.gridsize[1] // 2, self.own.start]])
+            else:
+                g = gidx[sel]
+            loc = g.astype(np.float64)
+            loc[:, 2] -= koff
+            return np.asfortranarray((loc * np.asarray(spacing, dtype=np.float64)[None, :]).astype(T))
+
+        tf = np.asfortranarray(shot.srcs.tf[:, isrc].astype(T)) if len(isrc) else np.zeros((nt, 1), dtype=T, order="F")
+        lshot = ScalarShot(srcs=ScalarSources(local_positions(gsrc, isrc), tf, shot.srcs.domfreq),
+                           recs=ScalarReceivers(local_positions(grec, irec), nt, dtype=self.params.dtype))
+        sim.init_shot(lshot)
+        sim.swforward_1shot(lshot)
+        full = np.zeros((nt, grec.shape[0]), dtype=self.params.dtype, order="F")
+        if len(irec):
+            full[:, irec] = lshot.recs.seismograms
+        if sp.world > 1:
+            full = sp.allreduce_host({"s": full})[0]["s"]
+        shot.recs.seismograms[...] = full
+        return full
+
+    def close(self):
+        self.sim.close()

@@ -108,3 +108,20 @@ def test_types_mirror_reference_checks():
     recs.seismograms[:] = 2.0
     assert m.calcmisfit(recs) == 20.0
     assert np.array_equal(m.dchi_du(recs), 2.0 * np.ones((5, 2)))
+
+
+def test_slab_partition_and_routing():
+    """host logic of the z-slab decomposition: contiguous cover, ghost planes, point routing"""
+    from swb200.multigpu import slab_local_planes, slab_range, slab_route_points
+
+    for nz, world in [(1024, 8), (61, 2), (90, 4), (75, 7)]:
+        owned = [slab_range(nz, world, r) for r in range(world)]
+        assert owned[0].start == 0 and owned[-1].stop == nz
+        assert all(owned[r].stop == owned[r + 1].start for r in range(world - 1))
+        assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+        for r in range(world):
+            loc = slab_local_planes(nz, world, r)
+            assert loc.start == owned[r].start - (r > 0) and loc.stop == owned[r].stop + (r < world - 1)
+        idx = np.stack([np.zeros(nz, dtype=np.int64), np.zeros(nz, dtype=np.int64), np.arange(nz)], axis=1)
+        routed = np.concatenate([slab_route_points(idx, nz, world, r) for r in range(world)])
+        assert sorted(routed.tolist()) == list(range(nz))  # every point has exactly one owner
