@@ -307,4 +307,15 @@ end
 # Multi-GPU shot sharding: one task per device, contiguous shot groups from distribsrcs (utils.jl:28-45); the per-device
 # totals are summed with swb_sim_allreduce_total_gradient (NCCL) -- see INTEGRATION.md for the run_swgradient! method.
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# z-slab decomposition of one 3D acoustic CD forward run (include/swb200.h section 4; no counterpart in the reference).
+# `model` is the slab-local simulation (owned planes + one ghost plane per interior face), `comm` a swb_comm handle created with
+# swb_comm_create; lower / upper = neighbour ranks, -1 at a true domain end.  Call before swforward_1shot!.
+# ---------------------------------------------------------------------------------------------------------------------
+function set_slab!(model::AcousticCDCPMLWaveSimulation{T, 3, <:B200Array}, comm::Ptr{Cvoid}, lower::Integer, upper::Integer) where {T}
+    check(ccall((:swb_sim_set_slab, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32), engine(model), comm, Int32(lower), Int32(upper)))
+    return model
+end
+
 end # module
