@@ -2,47 +2,135 @@
 //
 // The reference advances one step with four stencil sweeps that round-trip the stresses through memory
 // (src/models/elastic/backends/shared/elastic2D_iso_xPU.jl:1-79,120-239: update_σxx_σzz!, update_σxz!, update_ux!,
-// update_uz!; 19 array passes per cell) plus two tiny launches per source and per receiver.  The stresses are a pure
-// function of the current displacements (σ = C : ε(ucur), recomputed from scratch every step), so here a CTA
-//   1. requests every input of its TX x TZ tile at once: ux, uz plus a 4-cell halo and the stress-update factors into shared
-//      memory (cp.async), uold and the densities of the owned cells into registers,
-//   2. computes σxx, σzz, σxz on the tile plus a 2-cell halo into shared memory -- the halo is recomputed, not exchanged;
-//      the C-PML memory variables of the displacement derivatives are read from the `in` copy and written (owned cells
-//      only) to the `out` copy -- and applies the moment-tensor injection to its on-chip stresses,
-//   3. computes uxnew, uznew of the tile (with the C-PML memory variables of the stress derivatives) and stores them.
-// HBM traffic per cell-update: ux, uz read, uold read / unew written in place (4), λ, μ, μ_ihalf_jhalf, ρ_ihalf, ρ_jhalf
-// read = 11 values.  The arithmetic is the reference's, operation for operation: the derivative wrappers of
+// update_uz!; 19 array passes per cell) plus two tiny launches per source and per receiver, and one more full sweep for the
+// zero-lag correlations (elastic/backends/shared/correlate_gradient_xPU.jl:47-83).  The stresses are a pure function of
+// the current displacements (σ = C : ε(ucur), recomputed from scratch every step), so here a CTA
+//   1. has one thread request the whole shared-memory working set of its TX x TZ tile as TMA boxes (cp.async.bulk.tensor,
+//      one mbarrier): ux, uz plus a 4-cell halo; λ, μ, μ_ihalf_jhalf plus a 2-cell halo straight into the arrays that will
+//      hold σxx, σzz, σxz (each cell's factors are consumed by the thread that then overwrites them with that cell's
+//      stresses); for an adjoint launch that also correlates, the forward displacements u[it-1] plus a 2-cell halo.  uold and
+//      dt²/ρ of the owned cells go to registers meanwhile,
+//   2. computes σxx, σzz, σxz on the tile plus a 2-cell halo -- the halo is recomputed, not exchanged; the C-PML memory
+//      variables of the displacement derivatives are read from the `in` copy and written (owned cells only) to the `out`
+//      copy -- and applies the moment-tensor injection to its on-chip stresses; when correlating, the λ, μ, μ_ihalf_jhalf
+//      gradients are accumulated here, where the adjoint strain components are in registers anyway,
+//   3. computes uxnew, uznew of the tile (with the C-PML memory variables of the stress derivatives) and stores them;
+//      when correlating, accumulates the two ρ gradients.
+// A thread owns 16 bytes of consecutive cells (4 Float32 / 2 Float64) of one row: it reads whole vectors from shared memory
+// (x neighbours from the two adjacent vectors of the row, z neighbours from the same vector of the rows above / below) and, in
+// interior tiles (no C-PML strip, no grid edge, no free surface -- > 90 % of a production grid), moves its owned cells as one
+// 128-bit global access per array.  Tiles that touch a strip, an edge or the free surface run the same body with the
+// reference's range tests, mirrored free-surface rows and ∂̃ memory variables applied per cell.
+// HBM traffic per cell-update: ux, uz read, uold read / unew written in place (4), λ, μ, μ_ihalf_jhalf, dt²/ρ_ihalf,
+// dt²/ρ_jhalf read = 11 values; the correlation adds u[it-2], u[it-1], u[it] (6) and five accumulators read +
+// written (10).  The arithmetic is the reference's, operation for operation: the derivative wrappers of
 // freesurface_derivatives_4th_mirror.jl:1-244 (zero padding outside every array -- here literal zeros of the padded
 // planes --, odd / even mirroring and the Hooke's-law row at the free surface), ∂̃4th of src/utils/fdgenerated.jl:178-195,
-// stresses rounded to T before the displacement update reads them.
+// stresses rounded to T before the displacement update reads them.  (SWB_FLAG_FAST_F32 evaluates the 4-point derivative as
+// 27/24 (f3 - f2) + 1/24 (f1 - f4) and contracts a*b+c into FMAs; every other mode keeps the reference's operation order.)
 // External-force / adjoint-source injection and the receiver sums stay separate small launches (elf_inject_force,
-// elf_record); the zero-lag correlations run in elf_correlate on the same padded planes.
+// elf_record); elf_correlate is the stand-alone correlation (last adjoint step, step-by-step path).
 #include "ela_fused.h"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace swb {
 
+int elf_tz(int dtype)
+{
+    if (dtype == SWB_F64)
+        return 8;
+    static const int tz = [] {
+        const char *e = std::getenv("SWB_ELF_TZ");
+        const int v = e ? std::atoi(e) : 0;
+        return (v == 16 || v == 24) ? v : 16;
+    }();
+    return tz;
+}
+
+// 2D tensor map of a whole padded plane (all guard rows included), box = ELF_SW columns x box_rows rows
+void elf_make_tmap(CUtensorMap *out, int dtype, const void *plane_base, long long ld, long long rows, int box_rows)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SWB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
+            throw Error(SWB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        return (encode_fn)fn;
+    }();
+    const size_t es = dtype == SWB_F64 ? 8 : 4;
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld * es};
+    const cuuint32_t box[2] = {(cuuint32_t)ELF_SW, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, dtype == SWB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(plane_base), gdim, gstr, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        throw Error(SWB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+}
+
 namespace {
 
-constexpr int TX = ELF_TX, TZ = ELF_TZ, NTHR = 256;
-constexpr int UW = TX + 8;  // staged displacement rows: columns -4 .. TX+3
-constexpr int UH = TZ + 8;  // rows -4 .. TZ+3
-constexpr int SW = ELF_SW;  // stress rows: columns -2 .. TX+1
-constexpr int SH = TZ + 4;  // rows -2 .. TZ+1
+constexpr int TX = ELF_TX, NTHR = 256;
+constexpr int W = ELF_SW; // row pitch of every staged array: columns -4 .. TX+3
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
-template <class T>
-__device__ __forceinline__ void cp_async_chunk(T *smem, const T *gmem) // 4 elements
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
 {
-    cp_async16(smem, gmem);
-    if (sizeof(T) == 8)
-        cp_async16((char *)smem + 16, (const char *)gmem + 16);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}\n" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+// one TMA box: columns c0 .. c0 + ELF_SW - 1, rows c1 .. c1 + box_rows - 1 of a padded plane (zeros outside the plane)
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(smem_u32(dst)), "l"(map), "r"(c0),
+                 "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 16-byte vectors of consecutive cells
+__device__ __forceinline__ void ldv(const float *p, float (&o)[4])
+{
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
+}
+__device__ __forceinline__ void ldv(const double *p, double (&o)[2])
+{
+    const double2 v = *reinterpret_cast<const double2 *>(p);
+    o[0] = v.x, o[1] = v.y;
+}
+__device__ __forceinline__ void ldv_ro(const float *p, float (&o)[4])
+{
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
+}
+__device__ __forceinline__ void ldv_ro(const double *p, double (&o)[2])
+{
+    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+    o[0] = v.x, o[1] = v.y;
+}
+__device__ __forceinline__ void stv(float *p, const float (&o)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(o[0], o[1], o[2], o[3]); }
+__device__ __forceinline__ void stv(double *p, const double (&o)[2]) { *reinterpret_cast<double2 *>(p) = make_double2(o[0], o[1]); }
 
 // ∂x4th_inner / ∂y4th_inner (freesurface_derivatives_4th_mirror.jl:2-7)
 template <class T, class CT>
@@ -51,6 +139,27 @@ __device__ __forceinline__ CT inner4(T f1, T f2, T f3, T f4, T inv)
     const CT c1 = (CT)(1.0 / 24.0), c2 = (CT)(27.0 / 24.0);
     return (((c1 * (CT)f1 - c2 * (CT)f2) + c2 * (CT)f3) - c1 * (CT)f4) * (CT)inv;
 }
+template <>
+__device__ __forceinline__ float inner4<float, float>(float f1, float f2, float f3, float f4, float inv) // SWB_FLAG_FAST_F32
+{
+    return __fmaf_rn(1.125f * inv, f3 - f2, ((1.0f / 24.0f) * inv) * (f1 - f4));
+}
+// a * b + c: two roundings like the reference (the library is compiled with -fmad=false), one FMA under SWB_FLAG_FAST_F32
+template <class CT>
+__device__ __forceinline__ CT mad2(CT a, CT b, CT c, bool)
+{
+    return a * b + c;
+}
+__device__ __forceinline__ float mad2(float a, float b, float c, int) { return __fmaf_rn(a, b, c); }
+template <class T, class CT>
+struct FastSel {
+    typedef bool type;
+};
+template <>
+struct FastSel<float, float> {
+    typedef int type;
+};
+#define MAD(a, b, c) mad2((CT)(a), (CT)(b), (CT)(c), typename FastSel<T, CT>::type(0))
 
 // ∂̃4th (fdgenerated.jl:178-195) with separate in / out memory-variable arrays; `own`: this CTA owns the cell and stores psi
 template <class T, class CT>
@@ -74,209 +183,356 @@ __device__ __forceinline__ CT cpml4(CT D, int I, int ndim, int halo, bool half, 
     return r;
 }
 
-template <class T>
+template <class T, int TZ, bool ADJ>
 struct ElaSmem {
-    T ux[UH * UW], uz[UH * UW];                  // displacements, rows -4 .. TZ+3, columns -4 .. TX+3
-    T lam[SH * UW], mu[SH * UW], muhh[SH * UW];  // stress-update factors, rows -2 .. TZ+1, columns -4 .. TX+3
-    T sxx[SH * SW], szz[SH * SW], sxz[SH * SW];  // stresses, rows -2 .. TZ+1, columns -2 .. TX+1
+    static constexpr int UH = TZ + 8, SH = TZ + 4;
+    T ux[UH * W], uz[UH * W];                     // displacements, rows -4 .. TZ+3, columns -4 .. TX+3 (TMA destinations: 128-byte aligned)
+    T sxx[SH * W], szz[SH * W], sxz[SH * W];      // λ, μ, μ_ihalf_jhalf, then the stresses: rows -2 .. TZ+1
+    T fx[ADJ ? SH * W : 8], fz[ADJ ? SH * W : 8]; // forward u[it-1] for the correlation, rows -2 .. TZ+1
+    unsigned long long bar;
+    static_assert(TZ % 4 == 0, "rows x 544 bytes must be a multiple of 128");
 };
-constexpr int NP3 = TZ * TX / NTHR; // cells per thread in the displacement update (fixed mapping: column tid % TX, rows tid / TX + 2 n)
 
-template <class T, class CT, bool EDGE>
-__device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T> &S)
+// moment-tensor injection into the on-chip stresses (inject_momten_sources2D_σxx_σzz! / _σxz! :81-94)
+template <class T, int TZ, bool ADJ>
+__device__ __forceinline__ void inject_mt(const ElaFusedParams<T> &P, ElaSmem<T, TZ, ADJ> &S, int tile, int tid)
 {
+    if (P.mt_it <= 0)
+        return;
+    int e = P.mt_off[tile];
+    const int e1 = P.mt_off[tile + 1];
+    while (e < e1) { // sources in index order (they may share cells); the points of one source in parallel (distinct cells)
+        const int s = P.mt_src[e];
+        int en = e + 1;
+        while (en < e1 && P.mt_src[en] == s)
+            ++en;
+        const T w = P.srctf[(long long)s * P.nt + (P.mt_it - 1)];
+        for (int k = e + tid; k < en; k += NTHR) {
+            const int cell = P.mt_cell[k];
+            const T cf = P.mt_coef[k];
+            if (cell < ELF_MT_FIELD) {
+                S.sxx[cell] = S.sxx[cell] + (P.Mxx[s] * cf) * w;
+                S.szz[cell] = S.szz[cell] + (P.Mzz[s] * cf) * w;
+            } else
+                S.sxz[cell - ELF_MT_FIELD] = S.sxz[cell - ELF_MT_FIELD] + (P.Mxz[s] * cf) * w;
+        }
+        __syncthreads();
+        e = en;
+    }
+}
+
+// ---- the tile body -------------------------------------------------------------------------------------------------------------
+// EDGE = false: every cell of the tile's stress region lies inside all update ranges, outside every C-PML strip and below the
+// free-surface rows, so the reference's expressions reduce to the plain 4-point derivatives.  EDGE = true: the reference's
+// range tests, free-surface rows and ∂̃ memory variables per cell.  The two outermost vectors of a stress row (columns
+// -4 .. -1 and TX .. TX+3) hold two needed and two junk cells each; junk is computed from in-bounds shared memory and never read.
+template <class T, class CT, int TZ, bool ADJ, bool EDGE>
+__device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, TZ, ADJ> &S)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int NV = W / V;   // vectors per staged row
+    constexpr int NVT = TX / V; // vectors per tile row
+    constexpr int SH = TZ + 4, UH = TZ + 8;
+    constexpr int NP3 = TZ * NVT / NTHR; // vectors per thread in the displacement update
+    static_assert(TZ * NVT % NTHR == 0, "tile rows must split evenly over the CTA");
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TX, z0 = blockIdx.y * TZ;
     const int nx = P.nx, nz = P.nz, h = P.halo;
     const long long ld = P.ld;
     const bool ft = P.freetop != 0;
+    const int j0 = ft ? 1 : 2;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const T idx_ = P.inv_dx, idz_ = P.inv_dz;
 
-    // ---- phase 1: every input of the tile is requested before anything is computed, so that a CTA has its whole working set
-    //      in flight at once: ux, uz (+4-cell halo) and λ, μ, μ_ihalf_jhalf (+2 halo rows) -> shared memory with cp.async;
-    //      uold, ρ_ihalf, ρ_jhalf of the owned cells -> registers (used once, in phase 3)
-    for (int idx = tid; idx < UH * (UW / 4); idx += NTHR) {
-        const int r = idx / (UW / 4), ch = idx - r * (UW / 4);
-        const int gx = x0 - 4 + 4 * ch;
-        const long long q = (long long)(z0 - 4 + r) * ld + gx;
-        T *dx = S.ux + r * UW + 4 * ch, *dz = S.uz + r * UW + 4 * ch;
-        if (gx >= ld) { // beyond the row pitch (last tile of a row): zeros, like everything outside the arrays
-            dx[0] = dx[1] = dx[2] = dx[3] = (T)0;
-            dz[0] = dz[1] = dz[2] = dz[3] = (T)0;
-        } else {
-            cp_async_chunk(dx, P.uxc + q);
-            cp_async_chunk(dz, P.uzc + q);
+    // ---- phase 1: one thread requests the shared-memory working set (TMA), all threads their owned uold and dt²/ρ ----------
+    if (tid == 0) {
+        mbar_init(&S.bar, 1);
+        constexpr unsigned bytes = (unsigned)((2 * UH + (ADJ ? 5 : 3) * SH) * W * sizeof(T));
+        mbar_expect_tx(&S.bar, bytes);
+        tma_load_2d(S.ux, &P.tm[0], x0 - 4, ELF_GB + z0 - 4, &S.bar);
+        tma_load_2d(S.uz, &P.tm[1], x0 - 4, ELF_GB + z0 - 4, &S.bar);
+        tma_load_2d(S.sxx, &P.tm[2], x0 - 4, ELF_GB + z0 - 2, &S.bar);
+        tma_load_2d(S.szz, &P.tm[3], x0 - 4, ELF_GB + z0 - 2, &S.bar);
+        tma_load_2d(S.sxz, &P.tm[4], x0 - 4, ELF_GB + z0 - 2, &S.bar);
+        if (ADJ) {
+            tma_load_2d(S.fx, &P.tm[5], x0 - 4, ELF_GB + z0 - 2, &S.bar);
+            tma_load_2d(S.fz, &P.tm[6], x0 - 4, ELF_GB + z0 - 2, &S.bar);
         }
     }
-    for (int idx = tid; idx < SH * (UW / 4); idx += NTHR) {
-        const int r = idx / (UW / 4), ch = idx - r * (UW / 4);
-        const int gx = x0 - 4 + 4 * ch;
-        const long long q = (long long)(z0 - 2 + r) * ld + gx;
-        if (gx < ld) { // (factors beyond the pitch only feed cells that are masked out)
-            cp_async_chunk(S.lam + r * UW + 4 * ch, P.lam + q);
-            cp_async_chunk(S.mu + r * UW + 4 * ch, P.mu + q);
-            cp_async_chunk(S.muhh + r * UW + 4 * ch, P.mu_hh + q);
-        }
-    }
-    T r_uxo[NP3], r_uzo[NP3], r_ri[NP3], r_rj[NP3];
-    {
-        const int c = tid % TX, rb = tid / TX;
+    T r_uxo[NP3][V], r_uzo[NP3][V], r_fi[NP3][V], r_fj[NP3][V];
 #pragma unroll
-        for (int n = 0; n < NP3; ++n) { // all inside the padded plane (junk beyond the arrays is masked at the point of use)
-            const long long q = (long long)(z0 + rb + (NTHR / TX) * n) * ld + (x0 + c);
-            r_uxo[n] = P.uxo[q];
-            r_uzo[n] = P.uzo[q];
-            r_ri[n] = P.rho_ih[q];
-            r_rj[n] = P.rho_jh[q];
-        }
+    for (int n = 0; n < NP3; ++n) { // all inside the padded plane (junk beyond the arrays is masked at the point of use)
+        const int t = tid + NTHR * n;
+        const int r = t / NVT, v = t - r * NVT;
+        const long long q = (long long)(z0 + r) * ld + (x0 + v * V);
+        ldv(P.uxo + q, r_uxo[n]);
+        ldv(P.uzo + q, r_uzo[n]);
+        ldv_ro(P.fac_ih + q, r_fi[n]);
+        ldv_ro(P.fac_jh + q, r_fj[n]);
     }
-    cp_async_wait_all();
-    __syncthreads();
-
-#define UX(r, c) S.ux[((r) + 4) * UW + (c) + 4]
-#define UZ(r, c) S.uz[((r) + 4) * UW + (c) + 4]
-#define SXX(r, c) S.sxx[((r) + 2) * SW + (c) + 2]
-#define SZZ(r, c) S.szz[((r) + 2) * SW + (c) + 2]
-#define SXZ(r, c) S.sxz[((r) + 2) * SW + (c) + 2]
+    __syncthreads(); // (the mbarrier's initialisation becomes visible to the waiting threads)
+    mbar_wait(&S.bar, 0);
 
     // ---- phase 2: stresses on the tile + 2-cell halo (update_σxx_σzz! :39-60, update_σxz! :62-79) ------------------------
-    for (int idx = tid; idx < SH * SW; idx += NTHR) {
-        const int rr = idx / SW, cc = idx - rr * SW;
-        const int r = rr - 2, c = cc - 2;
-        const int I = x0 + c + 1, J = z0 + r + 1; // 1-based reference indices
-        const bool own = r >= 0 && r < TZ && c >= 0 && c < TX;
-        const int qm = rr * UW + c + 4; // this cell in the staged factor arrays
-        T sxx = (T)0, szz = (T)0, sxz = (T)0;
-        const int j0 = ft ? 1 : 2;
-        if (!EDGE || (I >= 2 && I <= nx - 1 && J >= j0 && J <= nz - 1)) {
-            const CT dudx = inner4<T, CT>(UX(r, c - 2), UX(r, c - 1), UX(r, c), UX(r, c + 1), P.inv_dx);
-            const T l = S.lam[qm], m = S.mu[qm];
-            CT dwdz;
+    for (int t = tid; t < SH * NV; t += NTHR) {
+        const int rr = t / NV, vv = t - rr * NV;
+        const int r = rr - 2, c0 = vv * V - 4; // first cell of the vector
+        const int ou = (rr + 2) * W + vv * V;  // ... in ux / uz
+        const int os = rr * W + vv * V;        // ... in the stress / factor / forward-field arrays
+        const int J = z0 + r + 1;              // 1-based reference row
+        T X[3][V], Z[3][V], xm1[V], xp1[V], xp2[V], zm2[V], zm1[V], zp1[V], l[V], m[V], mh[V];
+        ldv(S.ux + ou - V, X[0]);
+        ldv(S.ux + ou, X[1]);
+        ldv(S.ux + ou + V, X[2]);
+        ldv(S.uz + ou - V, Z[0]);
+        ldv(S.uz + ou, Z[1]);
+        ldv(S.uz + ou + V, Z[2]);
+        ldv(S.ux + ou - W, xm1);
+        ldv(S.ux + ou + W, xp1);
+        ldv(S.ux + ou + 2 * W, xp2);
+        ldv(S.uz + ou - 2 * W, zm2);
+        ldv(S.uz + ou - W, zm1);
+        ldv(S.uz + ou + W, zp1);
+        ldv(S.sxx + os, l);
+        ldv(S.szz + os, m);
+        ldv(S.sxz + os, mh);
+        const T *Xf = &X[0][0], *Zf = &Z[0][0]; // columns c0 - V .. c0 + 2 V - 1 of row r
+        T oxx[V], ozz[V], oxz[V];
+        CT dudx[V], dwdz[V], dwdx[V], dudz[V]; // before ∂̃: the adjoint strains of the correlation
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int c = c0 + k, I = x0 + c + 1;
+            bool v1 = true, v2 = true, own = true;
+            if (EDGE) {
+                const bool inreg = c >= -2 && c <= TX + 1;
+                v1 = inreg && I >= 2 && I <= nx - 1 && J >= j0 && J <= nz - 1;
+                v2 = inreg && I >= 1 && I <= nx - 1 && J >= 1 && J <= nz - 1;
+                own = r >= 0 && r < TZ && c >= 0 && c < TX;
+            }
+            dudx[k] = inner4<T, CT>(Xf[V + k - 2], Xf[V + k - 1], Xf[V + k], Xf[V + k + 1], idx_);
             if (EDGE && ft && J == 1) { // Hooke's law on the free-surface row (:179-195)
-                const T fac = -l / (l + (T)2 * m);
-                dwdz = (CT)fac * dudx;
-            } else if (EDGE && ft && J == 2)
-                dwdz = inner4<T, CT>(UZ(r - 1, c), UZ(r - 1, c), UZ(r, c), UZ(r + 1, c), P.inv_dz);
-            else
-                dwdz = inner4<T, CT>(UZ(r - 2, c), UZ(r - 1, c), UZ(r, c), UZ(r + 1, c), P.inv_dz);
-            CT dudx_c = dudx, dwdz_c = dwdz;
-            if (EDGE) {
-                dudx_c = cpml4<T, CT>(dudx, I - 1, nx - 1, h, true, P.a_x, P.b_x, P.psi_in[4], P.psi_out[4], (long long)(J - 1) * (2 * (h + 1)), 1, own);
-                dwdz_c = cpml4<T, CT>(dwdz, J - 1, nz - 1, h, true, P.a_z, P.b_z, P.psi_in[7], P.psi_out[7], (long long)(I - 1), nx, own);
+                const T fac = -l[k] / (l[k] + (T)2 * m[k]);
+                dwdz[k] = (CT)fac * dudx[k];
+            } else
+                dwdz[k] = inner4<T, CT>((EDGE && ft && J == 2) ? zm1[k] : zm2[k], zm1[k], Zf[V + k], zp1[k], idz_);
+            CT dudx_c = dudx[k], dwdz_c = dwdz[k];
+            if (EDGE && v1) {
+                dudx_c = cpml4<T, CT>(dudx[k], I - 1, nx - 1, h, true, P.a_x, P.b_x, P.psi_in[4], P.psi_out[4], (long long)(J - 1) * (2 * (h + 1)), 1, own);
+                dwdz_c = cpml4<T, CT>(dwdz[k], J - 1, nz - 1, h, true, P.a_z, P.b_z, P.psi_in[7], P.psi_out[7], (long long)(I - 1), nx, own);
             }
-            const T l2m = l + (T)2 * m;
-            sxx = (T)((CT)l2m * dudx_c + (CT)l * dwdz_c);
-            szz = (EDGE && J == 1) ? (T)0 : (T)((CT)l * dudx_c + (CT)l2m * dwdz_c);
-        }
-        if (!EDGE || (I >= 1 && I <= nx - 1 && J >= 1 && J <= nz - 1)) {
-            const CT dwdx = inner4<T, CT>(UZ(r, c - 1), UZ(r, c), UZ(r, c + 1), UZ(r, c + 2), P.inv_dx);
-            CT dudz;
-            if (EDGE && ft && J == 1) // even mirror of ux at the free surface (:214-222)
-                dudz = inner4<T, CT>(UX(r + 1, c), UX(r, c), UX(r + 1, c), UX(r + 2, c), P.inv_dz);
-            else
-                dudz = inner4<T, CT>(UX(r - 1, c), UX(r, c), UX(r + 1, c), UX(r + 2, c), P.inv_dz);
-            CT dwdx_c = dwdx, dudz_c = dudz;
-            if (EDGE) {
-                dwdx_c = cpml4<T, CT>(dwdx, I, nx, h, false, P.a_xh, P.b_xh, P.psi_in[5], P.psi_out[5], (long long)(J - 1) * (2 * h), 1, own);
-                dudz_c = cpml4<T, CT>(dudz, J, nz, h, false, P.a_zh, P.b_zh, P.psi_in[6], P.psi_out[6], (long long)(I - 1), nx - 1, own);
+            const T l2m = l[k] + (T)2 * m[k];
+            oxx[k] = (T)MAD(l2m, dudx_c, (CT)l[k] * dwdz_c);
+            ozz[k] = (EDGE && J == 1) ? (T)0 : (T)MAD(l[k], dudx_c, (CT)l2m * dwdz_c);
+            if (EDGE && !v1)
+                oxx[k] = ozz[k] = (T)0;
+            dwdx[k] = inner4<T, CT>(Zf[V + k - 1], Zf[V + k], Zf[V + k + 1], Zf[V + k + 2], idx_);
+            // (even mirror of ux at the free surface, :214-222)
+            dudz[k] = inner4<T, CT>((EDGE && ft && J == 1) ? xp1[k] : xm1[k], Xf[V + k], xp1[k], xp2[k], idz_);
+            CT dwdx_c = dwdx[k], dudz_c = dudz[k];
+            if (EDGE && v2) {
+                dwdx_c = cpml4<T, CT>(dwdx[k], I, nx, h, false, P.a_xh, P.b_xh, P.psi_in[5], P.psi_out[5], (long long)(J - 1) * (2 * h), 1, own);
+                dudz_c = cpml4<T, CT>(dudz[k], J, nz, h, false, P.a_zh, P.b_zh, P.psi_in[6], P.psi_out[6], (long long)(I - 1), nx - 1, own);
             }
-            sxz = (T)((CT)S.muhh[qm] * (dwdx_c + dudz_c));
+            oxz[k] = (T)((CT)mh[k] * (dwdx_c + dudz_c));
+            if (EDGE && !v2)
+                oxz[k] = (T)0;
         }
-        S.sxx[idx] = sxx;
-        S.szz[idx] = szz;
-        S.sxz[idx] = sxz;
+        stv(S.sxx + os, oxx);
+        stv(S.szz + os, ozz);
+        stv(S.sxz + os, oxz);
+        if (ADJ) { // grad_λ, grad_μ, grad_μ_ihalf_jhalf of the owned cells (correlate_gradient_xPU.jl:62-82)
+            if (r >= 0 && r < TZ && c0 >= 0 && c0 < TX) {
+                const long long q = (long long)(z0 + r) * ld + (x0 + c0);
+                T gl[V], gm[V], gh[V], F[3][V], G[3][V], fm1[V], fp1[V], fp2[V], gm2[V], gm1[V], gp1[V];
+                if (!EDGE) {
+                    ldv(P.g_l + q, gl);
+                    ldv(P.g_m + q, gm);
+                    ldv(P.g_mh + q, gh);
+                }
+                ldv(S.fx + os - V, F[0]);
+                ldv(S.fx + os, F[1]);
+                ldv(S.fx + os + V, F[2]);
+                ldv(S.fz + os - V, G[0]);
+                ldv(S.fz + os, G[1]);
+                ldv(S.fz + os + V, G[2]);
+                ldv(S.fx + os - W, fm1);
+                ldv(S.fx + os + W, fp1);
+                ldv(S.fx + os + 2 * W, fp2);
+                ldv(S.fz + os - 2 * W, gm2);
+                ldv(S.fz + os - W, gm1);
+                ldv(S.fz + os + W, gp1);
+                const T *Ff = &F[0][0], *Gf = &G[0][0];
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const int I = x0 + c0 + k + 1;
+                    const bool surf = EDGE && ft && J == 1;
+                    const bool v1 = !EDGE || (I >= 2 && I <= nx - 1 && J >= j0 && J <= nz - 1);
+                    const bool v2 = !EDGE || (I <= nx - 1 && J <= nz - 1);
+                    if (v1) {
+                        if (EDGE)
+                            gl[k] = P.g_l[q + k], gm[k] = P.g_m[q + k];
+                        const CT exx = inner4<T, CT>(Ff[V + k - 2], Ff[V + k - 1], Ff[V + k], Ff[V + k + 1], idx_);
+                        CT ezz;
+                        if (surf) {
+                            const T fac = -l[k] / (l[k] + (T)2 * m[k]);
+                            ezz = (CT)fac * exx;
+                        } else
+                            ezz = inner4<T, CT>((EDGE && ft && J == 2) ? gm1[k] : gm2[k], gm1[k], Gf[V + k], gp1[k], idz_);
+                        const CT exx_a = dudx[k], ezz_a = dwdz[k];
+                        const CT div_u = exx + ezz, div_a = exx_a + ezz_a;
+                        if (surf) {
+                            gl[k] = (T)((CT)gl[k] + (div_u * div_a) / (CT)2);
+                            gm[k] = (T)((CT)gm[k] + (exx * exx_a + ezz * ezz_a));
+                        } else {
+                            gl[k] = (T)((CT)gl[k] + div_u * div_a);
+                            gm[k] = (T)((CT)gm[k] + (CT)2 * (exx * exx_a + ezz * ezz_a));
+                        }
+                        if (EDGE)
+                            P.g_l[q + k] = gl[k], P.g_m[q + k] = gm[k];
+                    }
+                    if (v2) {
+                        if (EDGE)
+                            gh[k] = P.g_mh[q + k];
+                        const CT fdwdx = inner4<T, CT>(Gf[V + k - 1], Gf[V + k], Gf[V + k + 1], Gf[V + k + 2], idx_);
+                        const CT fdudz = inner4<T, CT>(surf ? fp1[k] : fm1[k], Ff[V + k], fp1[k], fp2[k], idz_);
+                        const CT exz = (fdwdx + fdudz) / (CT)2, exz_a = (dwdx[k] + dudz[k]) / (CT)2;
+                        gh[k] = (T)((CT)gh[k] + (CT)2 * (exz * exz_a + exz * exz_a));
+                        if (EDGE)
+                            P.g_mh[q + k] = gh[k];
+                    }
+                }
+                if (!EDGE) {
+                    stv(P.g_l + q, gl);
+                    stv(P.g_m + q, gm);
+                    stv(P.g_mh + q, gh);
+                }
+            }
+        }
     }
     __syncthreads();
-
-    // ---- moment-tensor injection into the on-chip stresses (inject_momten_sources2D_σxx_σzz! / _σxz! :81-94) --------------
-    if (P.mt_it > 0) {
-        int e = P.mt_off[tile];
-        const int e1 = P.mt_off[tile + 1];
-        while (e < e1) { // sources in index order (they may share cells); the points of one source in parallel (distinct cells)
-            const int s = P.mt_src[e];
-            int en = e + 1;
-            while (en < e1 && P.mt_src[en] == s)
-                ++en;
-            const T w = P.srctf[(long long)s * P.nt + (P.mt_it - 1)];
-            for (int k = e + tid; k < en; k += NTHR) {
-                const int cell = P.mt_cell[k];
-                const T cf = P.mt_coef[k];
-                if (cell < ELF_SREGION) {
-                    S.sxx[cell] = S.sxx[cell] + (P.Mxx[s] * cf) * w;
-                    S.szz[cell] = S.szz[cell] + (P.Mzz[s] * cf) * w;
-                } else
-                    S.sxz[cell - ELF_SREGION] = S.sxz[cell - ELF_SREGION] + (P.Mxz[s] * cf) * w;
-            }
-            __syncthreads();
-            e = en;
-        }
-    }
+    inject_mt<T, TZ, ADJ>(P, S, tile, tid);
 
     // ---- phase 3: displacements of the tile (update_ux! :1-18, update_uz! :20-37) -----------------------------------------
-    const T dt2 = P.dt * P.dt;
 #pragma unroll
     for (int n = 0; n < NP3; ++n) {
-        const int r = tid / TX + (NTHR / TX) * n, c = tid % TX;
-        const int I = x0 + c + 1, J = z0 + r + 1;
-        if (EDGE && (I > nx || J > nz))
-            continue;
-        const long long q = (long long)(z0 + r) * ld + (x0 + c);
-        if (!EDGE || I <= nx - 1) {
-            const CT d1 = inner4<T, CT>(SXX(r, c - 1), SXX(r, c), SXX(r, c + 1), SXX(r, c + 2), P.inv_dx);
-            CT d2;
+        const int t = tid + NTHR * n;
+        const int r = t / NVT, v = t - r * NVT;
+        const int c0 = v * V;
+        const int J = z0 + r + 1;
+        const long long q = (long long)(z0 + r) * ld + (x0 + c0);
+        const int os = (r + 2) * W + c0 + 4;
+        T A[3][V], B[3][V], bm2[V], bm1[V], bp1[V], zm1[V], z0v[V], zp1[V], zp2[V], ucx[V], ucz[V];
+        ldv(S.sxx + os - V, A[0]);
+        ldv(S.sxx + os, A[1]);
+        ldv(S.sxx + os + V, A[2]);
+        ldv(S.sxz + os - V, B[0]);
+        ldv(S.sxz + os, B[1]);
+        ldv(S.sxz + os + V, B[2]);
+        ldv(S.sxz + os - 2 * W, bm2);
+        ldv(S.sxz + os - W, bm1);
+        ldv(S.sxz + os + W, bp1);
+        ldv(S.szz + os - W, zm1);
+        ldv(S.szz + os, z0v);
+        ldv(S.szz + os + W, zp1);
+        ldv(S.szz + os + 2 * W, zp2);
+        ldv(S.ux + os + 2 * W, ucx);
+        ldv(S.uz + os + 2 * W, ucz);
+        const T *Af = &A[0][0], *Bf = &B[0][0];
+        T nx_[V], nz_[V];
+        bool vx[V], vz[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int I = x0 + c0 + k + 1;
+            vx[k] = !EDGE || (I <= nx - 1 && J <= nz);
+            vz[k] = !EDGE || (I <= nx && J <= nz - 1);
+            const CT a1 = inner4<T, CT>(Af[V + k - 1], Af[V + k], Af[V + k + 1], Af[V + k + 2], idx_);
+            CT a2;
             if (EDGE && ft && J == 1) // odd mirror of σxz at the free surface (:125-140)
-                d2 = inner4<T, CT>(-SXZ(r + 1, c), -SXZ(r, c), SXZ(r, c), SXZ(r + 1, c), P.inv_dz);
+                a2 = inner4<T, CT>(-bp1[k], -Bf[V + k], Bf[V + k], bp1[k], idz_);
             else if (EDGE && ft && J == 2)
-                d2 = inner4<T, CT>(-SXZ(r - 1, c), SXZ(r - 1, c), SXZ(r, c), SXZ(r + 1, c), P.inv_dz);
+                a2 = inner4<T, CT>(-bm1[k], bm1[k], Bf[V + k], bp1[k], idz_);
             else
-                d2 = inner4<T, CT>(SXZ(r - 2, c), SXZ(r - 1, c), SXZ(r, c), SXZ(r + 1, c), P.inv_dz);
-            CT c1 = d1, c2 = d2;
-            if (EDGE) {
-                c1 = cpml4<T, CT>(d1, I, nx, h, false, P.a_xh, P.b_xh, P.psi_in[0], P.psi_out[0], (long long)(J - 1) * (2 * h), 1, true);
-                c2 = cpml4<T, CT>(d2, J - 1, nz - 1, h, true, P.a_z, P.b_z, P.psi_in[3], P.psi_out[3], (long long)(I - 1), nx - 1, true);
+                a2 = inner4<T, CT>(bm2[k], bm1[k], Bf[V + k], bp1[k], idz_);
+            CT a1c = a1, a2c = a2;
+            if (EDGE && vx[k]) {
+                a1c = cpml4<T, CT>(a1, I, nx, h, false, P.a_xh, P.b_xh, P.psi_in[0], P.psi_out[0], (long long)(J - 1) * (2 * h), 1, true);
+                a2c = cpml4<T, CT>(a2, J - 1, nz - 1, h, true, P.a_z, P.b_z, P.psi_in[3], P.psi_out[3], (long long)(I - 1), nx - 1, true);
             }
-            const T t = (T)2 * UX(r, c) - r_uxo[n];
-            const T f = dt2 / r_ri[n];
-            P.uxn[q] = (T)((CT)t + (CT)f * (c1 + c2));
-        }
-        if (!EDGE || J <= nz - 1) {
-            const CT d1 = inner4<T, CT>(SXZ(r, c - 2), SXZ(r, c - 1), SXZ(r, c), SXZ(r, c + 1), P.inv_dx);
-            CT d2;
+            const T tx = fma((T)2, ucx[k], -r_uxo[n][k]); // = 2 ucur - uold rounded once (2 ucur is exact)
+            nx_[k] = (T)MAD(r_fi[n][k], a1c + a2c, tx);
+            const CT b1 = inner4<T, CT>(Bf[V + k - 2], Bf[V + k - 1], Bf[V + k], Bf[V + k + 1], idx_);
+            CT b2;
             if (EDGE && ft && J == 1) // odd mirror of σzz at the free surface (:85-93)
-                d2 = inner4<T, CT>(-SZZ(r + 1, c), SZZ(r, c), SZZ(r + 1, c), SZZ(r + 2, c), P.inv_dz);
+                b2 = inner4<T, CT>(-zp1[k], z0v[k], zp1[k], zp2[k], idz_);
             else
-                d2 = inner4<T, CT>(SZZ(r - 1, c), SZZ(r, c), SZZ(r + 1, c), SZZ(r + 2, c), P.inv_dz);
-            CT c1 = d1, c2 = d2;
-            if (EDGE) {
-                c1 = cpml4<T, CT>(d1, I - 1, nx - 1, h, true, P.a_x, P.b_x, P.psi_in[1], P.psi_out[1], (long long)(J - 1) * (2 * (h + 1)), 1, true);
-                c2 = cpml4<T, CT>(d2, J, nz, h, false, P.a_zh, P.b_zh, P.psi_in[2], P.psi_out[2], (long long)(I - 1), nx, true);
+                b2 = inner4<T, CT>(zm1[k], z0v[k], zp1[k], zp2[k], idz_);
+            CT b1c = b1, b2c = b2;
+            if (EDGE && vz[k]) {
+                b1c = cpml4<T, CT>(b1, I - 1, nx - 1, h, true, P.a_x, P.b_x, P.psi_in[1], P.psi_out[1], (long long)(J - 1) * (2 * (h + 1)), 1, true);
+                b2c = cpml4<T, CT>(b2, J, nz, h, false, P.a_zh, P.b_zh, P.psi_in[2], P.psi_out[2], (long long)(I - 1), nx, true);
             }
-            const T t = (T)2 * UZ(r, c) - r_uzo[n];
-            const T f = dt2 / r_rj[n];
-            P.uzn[q] = (T)((CT)t + (CT)f * (c1 + c2));
+            const T tz = fma((T)2, ucz[k], -r_uzo[n][k]);
+            nz_[k] = (T)MAD(r_fj[n][k], b1c + b2c, tz);
+        }
+        if (!EDGE) {
+            stv(P.uxn + q, nx_);
+            stv(P.uzn + q, nz_);
+        } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                if (vx[k])
+                    P.uxn[q + k] = nx_[k];
+                if (vz[k])
+                    P.uzn[q + k] = nz_[k];
+            }
+        }
+        if (ADJ) { // grad_ρ_ihalf, grad_ρ_jhalf (correlate_gradient_xPU.jl:50-60), all in T
+            T fxo[V], fzo[V], fxn[V], fzn[V], gi[V], gj[V], fcx[V], fcz[V];
+            ldv_ro(P.fxo + q, fxo);
+            ldv_ro(P.fzo + q, fzo);
+            ldv_ro(P.fxn + q, fxn);
+            ldv_ro(P.fzn + q, fzn);
+            ldv(P.g_ri + q, gi);
+            ldv(P.g_rj + q, gj);
+            ldv(S.fx + os, fcx);
+            ldv(S.fz + os, fcz);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const T vi = (ucx[k] * ((fxo[k] - (T)2 * fcx[k]) + fxn[k])) * P.inv_dt2;
+                gi[k] = gi[k] + ((EDGE && ft && J == 1) ? vi / (T)2 : vi);
+                gj[k] = gj[k] + (ucz[k] * ((fzo[k] - (T)2 * fcz[k]) + fzn[k])) * P.inv_dt2;
+            }
+            if (!EDGE) {
+                stv(P.g_ri + q, gi);
+                stv(P.g_rj + q, gj);
+            } else {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    if (vx[k])
+                        P.g_ri[q + k] = gi[k];
+                    if (vz[k])
+                        P.g_rj[q + k] = gj[k];
+                }
+            }
         }
     }
-#undef UX
-#undef UZ
-#undef SXX
-#undef SZZ
-#undef SXZ
 }
+#undef MAD
 
-template <class T, class CT>
-__global__ void __launch_bounds__(NTHR) ela_fused_kernel(const __grid_constant__ ElaFusedParams<T> P)
+template <class T, class CT, int TZ, bool ADJ>
+__global__ void __launch_bounds__(NTHR, 2) ela_fused_kernel(const __grid_constant__ ElaFusedParams<T> P)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    ElaSmem<T> &S = *reinterpret_cast<ElaSmem<T> *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ElaSmem<T, TZ, ADJ> &S = *reinterpret_cast<ElaSmem<T, TZ, ADJ> *>(smem_raw);
     const int x0 = blockIdx.x * TX, z0 = blockIdx.y * TZ;
     // interior tile: every cell of the tile's stress region (1-based indices x0-1 .. x0+TX+2, z0-1 .. z0+TZ+2) lies inside all
     // update ranges, outside every C-PML strip and below the free-surface rows
     const int m = max(P.halo + 1, 2);
     const bool interior = x0 - 1 > m && x0 + TX + 2 < P.nx - 1 - P.halo && z0 - 1 > m && z0 + TZ + 2 < P.nz - 1 - P.halo;
     if (interior)
-        ela_tile<T, CT, false>(P, S);
+        ela_tile<T, CT, TZ, ADJ, false>(P, S);
     else
-        ela_tile<T, CT, true>(P, S);
+        ela_tile<T, CT, TZ, ADJ, true>(P, S);
 }
 
 // ---- small kernels on the padded layout ---------------------------------------------------------------------------------
@@ -381,33 +637,77 @@ __global__ void __launch_bounds__(256) elf_correlate_kernel(int nx, int nz, int 
 }
 #undef PIX
 
+template <class T>
+__global__ void __launch_bounds__(256) elf_dt2_over_rho_kernel(long long ld, long long w, long long hgt, const T *rho, T *fac, T dt)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= w || j >= hgt)
+        return;
+    const T dt2 = dt * dt;
+    fac[j * ld + i] = dt2 / rho[j * ld + i];
+}
+
 } // namespace
 
-template <class T>
-void ela_fused_launch(const ElaFusedParams<T> &P, bool fast, cudaStream_t st)
+template <class T, class CT, int TZ, bool ADJ>
+static void ela_fused_launch_v(const ElaFusedParams<T> &P, cudaStream_t st)
 {
     const dim3 grd(cdiv(P.nx, TX), cdiv(P.nz, TZ), 1);
-    const size_t smem = sizeof(ElaSmem<T>);
+    const size_t smem = sizeof(ElaSmem<T, TZ, ADJ>);
     int dev = 0;
     SWB_CUDA(cudaGetDevice(&dev));
-    static bool done[2][64] = {}; // opt-in to > 48 KB of dynamic shared memory once per device and instantiation
-    const int v = (sizeof(T) == 4 && fast) ? 0 : 1;
-    if (dev < 64 && !done[v][dev]) {
-        if (v == 0)
-            SWB_CUDA(cudaFuncSetAttribute(ela_fused_kernel<T, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else
-            SWB_CUDA(cudaFuncSetAttribute(ela_fused_kernel<T, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        done[v][dev] = true;
+    static bool done[64] = {}; // opt-in to > 48 KB of dynamic shared memory once per device and instantiation
+    if (dev < 64 && !done[dev]) {
+        SWB_CUDA(cudaFuncSetAttribute(ela_fused_kernel<T, CT, TZ, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        done[dev] = true;
     }
-    if (v == 0)
-        ela_fused_kernel<T, T><<<grd, NTHR, smem, st>>>(P);
-    else
-        ela_fused_kernel<T, double><<<grd, NTHR, smem, st>>>(P);
+    ela_fused_kernel<T, CT, TZ, ADJ><<<grd, NTHR, smem, st>>>(P);
     check_launch("ela_fused_kernel");
     count_launch();
 }
-template void ela_fused_launch<float>(const ElaFusedParams<float> &, bool, cudaStream_t);
-template void ela_fused_launch<double>(const ElaFusedParams<double> &, bool, cudaStream_t);
+
+template <class T, class CT, int TZ>
+static void ela_fused_launch_a(const ElaFusedParams<T> &P, cudaStream_t st)
+{
+    if (P.corr)
+        ela_fused_launch_v<T, CT, TZ, true>(P, st);
+    else
+        ela_fused_launch_v<T, CT, TZ, false>(P, st);
+}
+
+template <>
+void ela_fused_launch<float>(const ElaFusedParams<float> &P, bool fast, cudaStream_t st)
+{
+    SWB_REQUIRE(P.tz == 16 || P.tz == 24, "fused elastic step: unsupported tile height");
+    if (fast) {
+        if (P.tz == 16)
+            ela_fused_launch_a<float, float, 16>(P, st);
+        else
+            ela_fused_launch_a<float, float, 24>(P, st);
+    } else {
+        if (P.tz == 16)
+            ela_fused_launch_a<float, double, 16>(P, st);
+        else
+            ela_fused_launch_a<float, double, 24>(P, st);
+    }
+}
+template <>
+void ela_fused_launch<double>(const ElaFusedParams<double> &P, bool, cudaStream_t st)
+{
+    SWB_REQUIRE(P.tz == 8, "fused elastic step: unsupported tile height");
+    ela_fused_launch_a<double, double, 8>(P, st);
+}
+
+void elf_dt2_over_rho(int dtype, long long ld, long long w, long long hgt, const void *rho, void *fac, double dt, cudaStream_t st)
+{
+    const dim3 grd(cdiv(w, 256), (unsigned)hgt, 1);
+    if (dtype == SWB_F64)
+        elf_dt2_over_rho_kernel<double><<<grd, 256, 0, st>>>(ld, w, hgt, (const double *)rho, (double *)fac, dt);
+    else
+        elf_dt2_over_rho_kernel<float><<<grd, 256, 0, st>>>(ld, w, hgt, (const float *)rho, (float *)fac, (float)dt);
+    check_launch("elf_dt2_over_rho");
+    count_launch();
+}
 
 void elf_inject_force(int dtype, long long ld, void *ux, void *uz, const void *rho_ih, const void *rho_jh, const swb_sinc_points &l0, const swb_sinc_points &l1,
                       const void *tf, long long nt, long long it, double dt, cudaStream_t st)

@@ -1,13 +1,16 @@
 // ela_fused.h -- parameter blocks and layout constants of the fused 2D elastic P-SV step (ela_fused.cu).
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
 
 namespace swb {
 
-constexpr int ELF_TX = 128; // tile width in cells
-constexpr int ELF_TZ = 16;  // tile height in cells
-constexpr int ELF_GB = 5;   // zero guard rows in front of a padded plane (4 halo rows + the left halo of row -4)
-constexpr int ELF_GA = ELF_TZ + 8; // zero guard rows behind it
+constexpr int ELF_TX = 128;    // tile width in cells
+constexpr int ELF_TZ_MAX = 32; // largest tile height any instantiation uses
+constexpr int ELF_GB = 5;      // zero guard rows in front of a padded plane (4 halo rows + the left halo of row -4)
+constexpr int ELF_GA = ELF_TZ_MAX + 8; // zero guard rows behind it
+// tile height in cells: chosen per storage type so that two CTAs (forward: three) fit the 227 KB of shared memory of an SM
+int elf_tz(int dtype);
 
 // Padded plane: row pitch ld >= nx + 8 (multiple of 32 elements): at least 4 zero columns after the last cell of a row
 // and 4 before the first cell of the next one, so the 4-point stencils of a tile's halo read zeros outside every
@@ -19,13 +22,16 @@ inline size_t elf_origin(long long nx) { return (size_t)elf_ld(nx) * ELF_GB; }
 
 template <class T>
 struct ElaFusedParams {
-    int nx, nz, halo, freetop;
+    // TMA descriptors of the padded planes staged through shared memory: ux, uz (current), λ, μ, μ_ihalf_jhalf, forward ux, uz [it-1]
+    alignas(64) CUtensorMap tm[7];
+    int nx, nz, halo, freetop, tz;
     long long ld;
     T inv_dx, inv_dz, dt;
     // padded planes, pointers to cell (1,1) of each array (ux: (nx-1, nz), uz: (nx, nz-1), ...)
     const T *uxc, *uzc, *uxo, *uzo;
     T *uxn, *uzn; // may alias uxo / uzo
-    const T *lam, *mu, *mu_hh, *rho_ih, *rho_jh;
+    // λ, μ, μ_ihalf_jhalf and the displacement-update factors dt^2 / ρ_ihalf, dt^2 / ρ_jhalf (zero outside their arrays)
+    const T *lam, *mu, *mu_hh, *fac_ih, *fac_jh;
     // C-PML memory variables, dense reference layouts (ela_models.jl:275-299), double-buffered because a tile recomputes
     // the stresses of its halo: 0 ψ_∂σxx∂x (2h, nz)  1 ψ_∂σxz∂x (2(h+1), nz-1)  2 ψ_∂σzz∂z (nx, 2h)  3 ψ_∂σxz∂z (nx-1, 2(h+1))
     //                           4 ψ_∂ux∂x (2(h+1), nz)  5 ψ_∂uz∂x (2h, nz-1)  6 ψ_∂ux∂z (nx-1, 2h)  7 ψ_∂uz∂z (nx, 2(h+1))
@@ -34,19 +40,34 @@ struct ElaFusedParams {
     const T *a_x, *a_xh, *b_x, *b_xh, *a_z, *a_zh, *b_z, *b_zh;
     // moment-tensor injection into the on-chip stresses: per-tile lists over the tile's stress region (tile + 2 halo cells),
     // entries grouped by source in index order.  mt_it = 0 disables.
-    const int *mt_off, *mt_cell, *mt_src; // cell = field * region + offset inside the region; field 0: σxx and σzz, 1: σxz
+    const int *mt_off, *mt_cell, *mt_src; // cell = field * ELF_MT_FIELD + offset inside the staged region; field 0: σxx and σzz, 1: σxz
     const T *mt_coef;
     const T *srctf, *Mxx, *Mzz, *Mxz;
     long long nt;
     int mt_it;
+    // zero-lag correlation fused into an adjoint launch (correlate_gradients!, elastic/backends/shared/
+    // correlate_gradient_xPU.jl:47-83): this launch's *current* adjoint field (the one the previous launch produced) against
+    // the forward displacements of three consecutive steps.  corr = 0 disables.
+    int corr;
+    const T *fxo, *fzo, *fxc, *fzc, *fxn, *fzn; // forward u[it-2], u[it-1], u[it]
+    T *g_ri, *g_rj, *g_l, *g_m, *g_mh;
+    T inv_dt2;
 };
 
 template <class T>
 void ela_fused_launch(const ElaFusedParams<T> &P, bool fast, cudaStream_t st);
+template <>
+void ela_fused_launch<float>(const ElaFusedParams<float> &P, bool fast, cudaStream_t st);
+template <>
+void ela_fused_launch<double>(const ElaFusedParams<double> &P, bool fast, cudaStream_t st);
 
-// region of on-chip stresses of a tile: rows -2 .. TZ+1, columns -2 .. TX+1
-constexpr int ELF_SW = ELF_TX + 4;
-constexpr int ELF_SREGION = (ELF_TZ + 4) * ELF_SW;
+// tensor map of a whole padded plane (plane_base = first guard row), box = ELF_SW columns x box_rows rows
+void elf_make_tmap(CUtensorMap *out, int dtype, const void *plane_base, long long ld, long long rows, int box_rows);
+
+// staged region of a tile in shared memory: rows -2 .. TZ+1 (stresses; displacements -4 .. TZ+3), columns -4 .. TX+3
+constexpr int ELF_SW = ELF_TX + 8;
+constexpr int ELF_MT_FIELD = 1 << 24;
+inline int elf_mt_cell(int field, int r, int c) { return field * ELF_MT_FIELD + (r + 2) * ELF_SW + (c + 4); }
 
 // small kernels on the padded layout (sinc lists as uploaded by the engine: 1-based (i, j) into the array they address)
 // external-force / adjoint-source injection into unew (elastic2D_iso_xPU.jl:96-106), sources in index order
@@ -55,6 +76,9 @@ void elf_inject_force(int dtype, long long ld, void *ux, void *uz, const void *r
 // traces[it, c, r] = sum_p coef[p] * u[ij[p]] (elastic2D_iso_xPU.jl:108-118, 219-230)
 void elf_record(int dtype, long long ld, const void *ux, const void *uz, const swb_sinc_points &lx, const swb_sinc_points &lz, void *traces, long long nt,
                 long long it, cudaStream_t st);
+// fac[q] = dt^2 / rho[q] on the (w, hgt) cells of a padded plane (the factor update_ux! / update_uz! compute per cell and
+// step, elastic2D_iso_xPU.jl:1-37), everything else of the plane stays zero
+void elf_dt2_over_rho(int dtype, long long ld, long long w, long long hgt, const void *rho, void *fac, double dt, cudaStream_t st);
 // correlate_gradients! (elastic/backends/shared/correlate_gradient_xPU.jl:1-83) on padded planes
 struct ElaCorrPadded {
     int dtype, flags, nx, nz, freetop;
