@@ -226,6 +226,17 @@ __device__ __forceinline__ void inject_mt(const ElaFusedParams<T> &P, ElaSmem<T,
 // free-surface rows, so the reference's expressions reduce to the plain 4-point derivatives.  EDGE = true: the reference's
 // range tests, free-surface rows and ∂̃ memory variables per cell.  The two outermost vectors of a stress row (columns
 // -4 .. -1 and TX .. TX+3) hold two needed and two junk cells each; junk is computed from in-bounds shared memory and never read.
+// Tile rows are issued bottom strip rows first, then from the top: the rows that touch the bottom C-PML strip run the slow
+// per-cell body and would otherwise form a tail of long CTAs at the end of the grid.
+template <int TZ>
+__device__ __forceinline__ int tile_row(int halo)
+{
+    const int nty = (int)gridDim.y;
+    const int nedge = min(nty, (halo + TZ + 3 + TZ - 1) / TZ);
+    const int by = (int)blockIdx.y + nty - nedge;
+    return by >= nty ? by - nty : by;
+}
+
 template <class T, class CT, int TZ, bool ADJ, bool EDGE>
 __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, TZ, ADJ> &S)
 {
@@ -236,13 +247,18 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
     constexpr int NP3 = TZ * NVT / NTHR; // vectors per thread in the displacement update
     static_assert(TZ * NVT % NTHR == 0, "tile rows must split evenly over the CTA");
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TX, z0 = blockIdx.y * TZ;
+    const int trow = tile_row<TZ>(P.halo);
+    const int x0 = blockIdx.x * TX, z0 = trow * TZ;
     const int nx = P.nx, nz = P.nz, h = P.halo;
     const long long ld = P.ld;
     const bool ft = P.freetop != 0;
     const int j0 = ft ? 1 : 2;
-    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int tile = trow * gridDim.x + blockIdx.x;
     const T idx_ = P.inv_dx, idz_ = P.inv_dz;
+    // does the tile's stress region reach an x / a z strip (or edge)?  ∂̃ is the identity elsewhere (CTA-uniform tests)
+    const int mm = max(h + 1, 2);
+    const bool xs = EDGE && !(x0 - 1 > mm && x0 + TX + 2 < nx - 1 - h);
+    const bool zs = EDGE && !(z0 - 1 > mm && z0 + TZ + 2 < nz - 1 - h);
 
     // ---- phase 1: one thread requests the shared-memory working set (TMA), all threads their owned uold and dt²/ρ ----------
     if (tid == 0) {
@@ -317,8 +333,10 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
                 dwdz[k] = inner4<T, CT>((EDGE && ft && J == 2) ? zm1[k] : zm2[k], zm1[k], Zf[V + k], zp1[k], idz_);
             CT dudx_c = dudx[k], dwdz_c = dwdz[k];
             if (EDGE && v1) {
-                dudx_c = cpml4<T, CT>(dudx[k], I - 1, nx - 1, h, true, P.a_x, P.b_x, P.psi_in[4], P.psi_out[4], (long long)(J - 1) * (2 * (h + 1)), 1, own);
-                dwdz_c = cpml4<T, CT>(dwdz[k], J - 1, nz - 1, h, true, P.a_z, P.b_z, P.psi_in[7], P.psi_out[7], (long long)(I - 1), nx, own);
+                if (xs)
+                    dudx_c = cpml4<T, CT>(dudx[k], I - 1, nx - 1, h, true, P.a_x, P.b_x, P.psi_in[4], P.psi_out[4], (long long)(J - 1) * (2 * (h + 1)), 1, own);
+                if (zs)
+                    dwdz_c = cpml4<T, CT>(dwdz[k], J - 1, nz - 1, h, true, P.a_z, P.b_z, P.psi_in[7], P.psi_out[7], (long long)(I - 1), nx, own);
             }
             const T l2m = l[k] + (T)2 * m[k];
             oxx[k] = (T)MAD(l2m, dudx_c, (CT)l[k] * dwdz_c);
@@ -330,8 +348,10 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
             dudz[k] = inner4<T, CT>((EDGE && ft && J == 1) ? xp1[k] : xm1[k], Xf[V + k], xp1[k], xp2[k], idz_);
             CT dwdx_c = dwdx[k], dudz_c = dudz[k];
             if (EDGE && v2) {
-                dwdx_c = cpml4<T, CT>(dwdx[k], I, nx, h, false, P.a_xh, P.b_xh, P.psi_in[5], P.psi_out[5], (long long)(J - 1) * (2 * h), 1, own);
-                dudz_c = cpml4<T, CT>(dudz[k], J, nz, h, false, P.a_zh, P.b_zh, P.psi_in[6], P.psi_out[6], (long long)(I - 1), nx - 1, own);
+                if (xs)
+                    dwdx_c = cpml4<T, CT>(dwdx[k], I, nx, h, false, P.a_xh, P.b_xh, P.psi_in[5], P.psi_out[5], (long long)(J - 1) * (2 * h), 1, own);
+                if (zs)
+                    dudz_c = cpml4<T, CT>(dudz[k], J, nz, h, false, P.a_zh, P.b_zh, P.psi_in[6], P.psi_out[6], (long long)(I - 1), nx - 1, own);
             }
             oxz[k] = (T)((CT)mh[k] * (dwdx_c + dudz_c));
             if (EDGE && !v2)
@@ -455,8 +475,10 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
                 a2 = inner4<T, CT>(bm2[k], bm1[k], Bf[V + k], bp1[k], idz_);
             CT a1c = a1, a2c = a2;
             if (EDGE && vx[k]) {
-                a1c = cpml4<T, CT>(a1, I, nx, h, false, P.a_xh, P.b_xh, P.psi_in[0], P.psi_out[0], (long long)(J - 1) * (2 * h), 1, true);
-                a2c = cpml4<T, CT>(a2, J - 1, nz - 1, h, true, P.a_z, P.b_z, P.psi_in[3], P.psi_out[3], (long long)(I - 1), nx - 1, true);
+                if (xs)
+                    a1c = cpml4<T, CT>(a1, I, nx, h, false, P.a_xh, P.b_xh, P.psi_in[0], P.psi_out[0], (long long)(J - 1) * (2 * h), 1, true);
+                if (zs)
+                    a2c = cpml4<T, CT>(a2, J - 1, nz - 1, h, true, P.a_z, P.b_z, P.psi_in[3], P.psi_out[3], (long long)(I - 1), nx - 1, true);
             }
             const T tx = fma((T)2, ucx[k], -r_uxo[n][k]); // = 2 ucur - uold rounded once (2 ucur is exact)
             nx_[k] = (T)MAD(r_fi[n][k], a1c + a2c, tx);
@@ -468,8 +490,10 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
                 b2 = inner4<T, CT>(zm1[k], z0v[k], zp1[k], zp2[k], idz_);
             CT b1c = b1, b2c = b2;
             if (EDGE && vz[k]) {
-                b1c = cpml4<T, CT>(b1, I - 1, nx - 1, h, true, P.a_x, P.b_x, P.psi_in[1], P.psi_out[1], (long long)(J - 1) * (2 * (h + 1)), 1, true);
-                b2c = cpml4<T, CT>(b2, J, nz, h, false, P.a_zh, P.b_zh, P.psi_in[2], P.psi_out[2], (long long)(I - 1), nx, true);
+                if (xs)
+                    b1c = cpml4<T, CT>(b1, I - 1, nx - 1, h, true, P.a_x, P.b_x, P.psi_in[1], P.psi_out[1], (long long)(J - 1) * (2 * (h + 1)), 1, true);
+                if (zs)
+                    b2c = cpml4<T, CT>(b2, J, nz, h, false, P.a_zh, P.b_zh, P.psi_in[2], P.psi_out[2], (long long)(I - 1), nx, true);
             }
             const T tz = fma((T)2, ucz[k], -r_uzo[n][k]);
             nz_[k] = (T)MAD(r_fj[n][k], b1c + b2c, tz);
@@ -516,6 +540,36 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
             }
         }
     }
+
+    // ---- external forces / adjoint sources on the owned cells, sources in index order (they may share cells) -----------------
+    if (P.fi_it > 0) {
+        int e = P.fi_off[tile];
+        const int e1 = P.fi_off[tile + 1];
+        if (e < e1) {
+            __syncthreads(); // the tile's unew is in memory
+            const T dt2 = P.dt * P.dt;
+            while (e < e1) {
+                const int s_ = P.fi_src[e];
+                int en = e + 1;
+                while (en < e1 && P.fi_src[en] == s_)
+                    ++en;
+                const T wx = P.fi_tf[((long long)s_ * 2 + 0) * P.nt + (P.fi_it - 1)], wz = P.fi_tf[((long long)s_ * 2 + 1) * P.nt + (P.fi_it - 1)];
+                for (int k = e + tid; k < en; k += NTHR) {
+                    const int cell = P.fi_cell[k];
+                    const int comp = cell >= ELF_MT_FIELD ? 1 : 0;
+                    const int o = cell - comp * ELF_MT_FIELD;
+                    const long long q = (long long)(z0 + o / TX) * ld + (x0 + o % TX);
+                    const T cf = P.fi_coef[k];
+                    if (comp == 0)
+                        P.uxn[q] = P.uxn[q] + ((cf * wx) / P.rho_ih[q]) * dt2;
+                    else
+                        P.uzn[q] = P.uzn[q] + ((cf * wz) / P.rho_jh[q]) * dt2;
+                }
+                __syncthreads();
+                e = en;
+            }
+        }
+    }
 }
 #undef MAD
 
@@ -524,7 +578,7 @@ __global__ void __launch_bounds__(NTHR, 2) ela_fused_kernel(const __grid_constan
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ElaSmem<T, TZ, ADJ> &S = *reinterpret_cast<ElaSmem<T, TZ, ADJ> *>(smem_raw);
-    const int x0 = blockIdx.x * TX, z0 = blockIdx.y * TZ;
+    const int x0 = blockIdx.x * TX, z0 = tile_row<TZ>(P.halo) * TZ;
     // interior tile: every cell of the tile's stress region (1-based indices x0-1 .. x0+TX+2, z0-1 .. z0+TZ+2) lies inside all
     // update ranges, outside every C-PML strip and below the free-surface rows
     const int m = max(P.halo + 1, 2);

@@ -45,6 +45,12 @@ struct ElaFusedParams {
     const T *srctf, *Mxx, *Mzz, *Mxz;
     long long nt;
     int mt_it;
+    // external-force / adjoint-source injection into the freshly stored unew (inject_external_sources2D! and the residual
+    // injection of adjoint_onestep_CPML!, elastic2D_iso_xPU.jl:96-106,433-440): per-tile lists over the owned cells, grouped
+    // by source in index order; cell = component * ELF_MT_FIELD + row * ELF_TX + column.  fi_it = 0 disables.
+    const int *fi_off, *fi_cell, *fi_src;
+    const T *fi_coef, *fi_tf, *rho_ih, *rho_jh;
+    int fi_it;
     // zero-lag correlation fused into an adjoint launch (correlate_gradients!, elastic/backends/shared/
     // correlate_gradient_xPU.jl:47-83): this launch's *current* adjoint field (the one the previous launch produced) against
     // the forward displacements of three consecutive steps.  corr = 0 disables.
