@@ -183,6 +183,47 @@ __device__ __forceinline__ CT cpml4(CT D, int I, int ndim, int halo, bool half, 
     return r;
 }
 
+// ∂̃4th for a whole vector of cells, split into an index step, a fetch step and a finish step so that the loads of every cell and
+// of both derivative kinds of a group are in flight together (the per-cell form above serialises one dependent global load per
+// cell and kind).  kk = 1-based index into the strip's memory variable / coefficient profiles, 0 = outside the strips (∂̃ = ∂).
+__device__ __forceinline__ int cpml_k(int I, int ndim, int halo, int p1)
+{
+    const int idim = I + p1;
+    if (idim <= halo + p1)
+        return idim;
+    if (idim >= ndim - halo)
+        return I - (ndim - halo) + 1 + (halo + p1);
+    return 0;
+}
+template <class T, int V>
+struct CpmlVec {
+    T a[V], b[V], psi[V];
+};
+template <class T, int V>
+__device__ __forceinline__ void cpml_fetch(CpmlVec<T, V> &c, const int (&kk)[V], const int (&off)[V], const T *__restrict__ a, const T *__restrict__ b,
+                                           const T *__restrict__ psi_in)
+{
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const bool in = kk[k] > 0;
+        c.a[k] = in ? a[kk[k] - 1] : (T)0;
+        c.b[k] = in ? b[kk[k] - 1] : (T)0;
+        c.psi[k] = in ? psi_in[off[k]] : (T)0;
+    }
+}
+template <class T, class CT, int V>
+__device__ __forceinline__ void cpml_finish(CT (&D)[V], const CpmlVec<T, V> &c, const int (&kk)[V], const int (&off)[V], const bool (&st)[V], T *__restrict__ psi_out)
+{
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+        if (kk[k] > 0) {
+            T pn;
+            D[k] = cpml_apply<T, CT>(D[k], c.a[k], c.b[k], c.psi[k], pn);
+            if (st[k])
+                psi_out[off[k]] = pn;
+        }
+}
+
 template <class T, int TZ, bool ADJ>
 struct ElaSmem {
     static constexpr int UH = TZ + 8, SH = TZ + 4;
@@ -315,15 +356,15 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
         const T *Xf = &X[0][0], *Zf = &Z[0][0]; // columns c0 - V .. c0 + 2 V - 1 of row r
         T oxx[V], ozz[V], oxz[V];
         CT dudx[V], dwdz[V], dwdx[V], dudz[V]; // before ∂̃: the adjoint strains of the correlation
+        bool v1[V], v2[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const int c = c0 + k, I = x0 + c + 1;
-            bool v1 = true, v2 = true, own = true;
+            v1[k] = v2[k] = true;
             if (EDGE) {
                 const bool inreg = c >= -2 && c <= TX + 1;
-                v1 = inreg && I >= 2 && I <= nx - 1 && J >= j0 && J <= nz - 1;
-                v2 = inreg && I >= 1 && I <= nx - 1 && J >= 1 && J <= nz - 1;
-                own = r >= 0 && r < TZ && c >= 0 && c < TX;
+                v1[k] = inreg && I >= 2 && I <= nx - 1 && J >= j0 && J <= nz - 1;
+                v2[k] = inreg && I >= 1 && I <= nx - 1 && J >= 1 && J <= nz - 1;
             }
             dudx[k] = inner4<T, CT>(Xf[V + k - 2], Xf[V + k - 1], Xf[V + k], Xf[V + k + 1], idx_);
             if (EDGE && ft && J == 1) { // Hooke's law on the free-surface row (:179-195)
@@ -331,30 +372,54 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
                 dwdz[k] = (CT)fac * dudx[k];
             } else
                 dwdz[k] = inner4<T, CT>((EDGE && ft && J == 2) ? zm1[k] : zm2[k], zm1[k], Zf[V + k], zp1[k], idz_);
-            CT dudx_c = dudx[k], dwdz_c = dwdz[k];
-            if (EDGE && v1) {
-                if (xs)
-                    dudx_c = cpml4<T, CT>(dudx[k], I - 1, nx - 1, h, true, P.a_x, P.b_x, P.psi_in[4], P.psi_out[4], (long long)(J - 1) * (2 * (h + 1)), 1, own);
-                if (zs)
-                    dwdz_c = cpml4<T, CT>(dwdz[k], J - 1, nz - 1, h, true, P.a_z, P.b_z, P.psi_in[7], P.psi_out[7], (long long)(I - 1), nx, own);
-            }
-            const T l2m = l[k] + (T)2 * m[k];
-            oxx[k] = (T)MAD(l2m, dudx_c, (CT)l[k] * dwdz_c);
-            ozz[k] = (EDGE && J == 1) ? (T)0 : (T)MAD(l[k], dudx_c, (CT)l2m * dwdz_c);
-            if (EDGE && !v1)
-                oxx[k] = ozz[k] = (T)0;
             dwdx[k] = inner4<T, CT>(Zf[V + k - 1], Zf[V + k], Zf[V + k + 1], Zf[V + k + 2], idx_);
             // (even mirror of ux at the free surface, :214-222)
             dudz[k] = inner4<T, CT>((EDGE && ft && J == 1) ? xp1[k] : xm1[k], Xf[V + k], xp1[k], xp2[k], idz_);
-            CT dwdx_c = dwdx[k], dudz_c = dudz[k];
-            if (EDGE && v2) {
-                if (xs)
-                    dwdx_c = cpml4<T, CT>(dwdx[k], I, nx, h, false, P.a_xh, P.b_xh, P.psi_in[5], P.psi_out[5], (long long)(J - 1) * (2 * h), 1, own);
-                if (zs)
-                    dudz_c = cpml4<T, CT>(dudz[k], J, nz, h, false, P.a_zh, P.b_zh, P.psi_in[6], P.psi_out[6], (long long)(I - 1), nx - 1, own);
+        }
+        CT dudx_c[V], dwdz_c[V], dwdx_c[V], dudz_c[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            dudx_c[k] = dudx[k], dwdz_c[k] = dwdz[k], dwdx_c[k] = dwdx[k], dudz_c[k] = dudz[k];
+        if (EDGE) { // ∂̃: ψ_∂ux∂x (4), ψ_∂uz∂z (7) for σxx, σzz; ψ_∂uz∂x (5), ψ_∂ux∂z (6) for σxz
+            int ka[V], kb[V], oa[V], ob[V];
+            bool st[V];
+            CpmlVec<T, V> ca, cb;
+            const int kz7 = zs ? cpml_k(J - 1, nz - 1, h, 1) : 0, kz6 = zs ? cpml_k(J, nz, h, 0) : 0;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int c = c0 + k, I = x0 + c + 1;
+                st[k] = r >= 0 && r < TZ && c >= 0 && c < TX;
+                ka[k] = (xs && v1[k]) ? cpml_k(I - 1, nx - 1, h, 1) : 0;
+                oa[k] = (J - 1) * (2 * (h + 1)) + (ka[k] - 1);
+                kb[k] = v1[k] ? kz7 : 0;
+                ob[k] = (I - 1) + (kz7 - 1) * nx;
             }
-            oxz[k] = (T)((CT)mh[k] * (dwdx_c + dudz_c));
-            if (EDGE && !v2)
+            cpml_fetch<T, V>(ca, ka, oa, P.a_x, P.b_x, P.psi_in[4]);
+            cpml_fetch<T, V>(cb, kb, ob, P.a_z, P.b_z, P.psi_in[7]);
+            cpml_finish<T, CT, V>(dudx_c, ca, ka, oa, st, P.psi_out[4]);
+            cpml_finish<T, CT, V>(dwdz_c, cb, kb, ob, st, P.psi_out[7]);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int I = x0 + c0 + k + 1;
+                ka[k] = (xs && v2[k]) ? cpml_k(I, nx, h, 0) : 0;
+                oa[k] = (J - 1) * (2 * h) + (ka[k] - 1);
+                kb[k] = v2[k] ? kz6 : 0;
+                ob[k] = (I - 1) + (kz6 - 1) * (nx - 1);
+            }
+            cpml_fetch<T, V>(ca, ka, oa, P.a_xh, P.b_xh, P.psi_in[5]);
+            cpml_fetch<T, V>(cb, kb, ob, P.a_zh, P.b_zh, P.psi_in[6]);
+            cpml_finish<T, CT, V>(dwdx_c, ca, ka, oa, st, P.psi_out[5]);
+            cpml_finish<T, CT, V>(dudz_c, cb, kb, ob, st, P.psi_out[6]);
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const T l2m = l[k] + (T)2 * m[k];
+            oxx[k] = (T)MAD(l2m, dudx_c[k], (CT)l[k] * dwdz_c[k]);
+            ozz[k] = (EDGE && J == 1) ? (T)0 : (T)MAD(l[k], dudx_c[k], (CT)l2m * dwdz_c[k]);
+            oxz[k] = (T)((CT)mh[k] * (dwdx_c[k] + dudz_c[k]));
+            if (EDGE && !v1[k])
+                oxx[k] = ozz[k] = (T)0;
+            if (EDGE && !v2[k])
                 oxz[k] = (T)0;
         }
         stv(S.sxx + os, oxx);
@@ -386,9 +451,9 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
                 for (int k = 0; k < V; ++k) {
                     const int I = x0 + c0 + k + 1;
                     const bool surf = EDGE && ft && J == 1;
-                    const bool v1 = !EDGE || (I >= 2 && I <= nx - 1 && J >= j0 && J <= nz - 1);
-                    const bool v2 = !EDGE || (I <= nx - 1 && J <= nz - 1);
-                    if (v1) {
+                    const bool w1 = !EDGE || (I >= 2 && I <= nx - 1 && J >= j0 && J <= nz - 1);
+                    const bool w2 = !EDGE || (I <= nx - 1 && J <= nz - 1);
+                    if (w1) {
                         if (EDGE)
                             gl[k] = P.g_l[q + k], gm[k] = P.g_m[q + k];
                         const CT exx = inner4<T, CT>(Ff[V + k - 2], Ff[V + k - 1], Ff[V + k], Ff[V + k + 1], idx_);
@@ -410,7 +475,7 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
                         if (EDGE)
                             P.g_l[q + k] = gl[k], P.g_m[q + k] = gm[k];
                     }
-                    if (v2) {
+                    if (w2) {
                         if (EDGE)
                             gh[k] = P.g_mh[q + k];
                         const CT fdwdx = inner4<T, CT>(Gf[V + k - 1], Gf[V + k], Gf[V + k + 1], Gf[V + k + 2], idx_);
@@ -460,43 +525,60 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
         const T *Af = &A[0][0], *Bf = &B[0][0];
         T nx_[V], nz_[V];
         bool vx[V], vz[V];
+        CT a1[V], a2[V], b1[V], b2[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const int I = x0 + c0 + k + 1;
             vx[k] = !EDGE || (I <= nx - 1 && J <= nz);
             vz[k] = !EDGE || (I <= nx && J <= nz - 1);
-            const CT a1 = inner4<T, CT>(Af[V + k - 1], Af[V + k], Af[V + k + 1], Af[V + k + 2], idx_);
-            CT a2;
+            a1[k] = inner4<T, CT>(Af[V + k - 1], Af[V + k], Af[V + k + 1], Af[V + k + 2], idx_);
             if (EDGE && ft && J == 1) // odd mirror of σxz at the free surface (:125-140)
-                a2 = inner4<T, CT>(-bp1[k], -Bf[V + k], Bf[V + k], bp1[k], idz_);
+                a2[k] = inner4<T, CT>(-bp1[k], -Bf[V + k], Bf[V + k], bp1[k], idz_);
             else if (EDGE && ft && J == 2)
-                a2 = inner4<T, CT>(-bm1[k], bm1[k], Bf[V + k], bp1[k], idz_);
+                a2[k] = inner4<T, CT>(-bm1[k], bm1[k], Bf[V + k], bp1[k], idz_);
             else
-                a2 = inner4<T, CT>(bm2[k], bm1[k], Bf[V + k], bp1[k], idz_);
-            CT a1c = a1, a2c = a2;
-            if (EDGE && vx[k]) {
-                if (xs)
-                    a1c = cpml4<T, CT>(a1, I, nx, h, false, P.a_xh, P.b_xh, P.psi_in[0], P.psi_out[0], (long long)(J - 1) * (2 * h), 1, true);
-                if (zs)
-                    a2c = cpml4<T, CT>(a2, J - 1, nz - 1, h, true, P.a_z, P.b_z, P.psi_in[3], P.psi_out[3], (long long)(I - 1), nx - 1, true);
-            }
-            const T tx = fma((T)2, ucx[k], -r_uxo[n][k]); // = 2 ucur - uold rounded once (2 ucur is exact)
-            nx_[k] = (T)MAD(r_fi[n][k], a1c + a2c, tx);
-            const CT b1 = inner4<T, CT>(Bf[V + k - 2], Bf[V + k - 1], Bf[V + k], Bf[V + k + 1], idx_);
-            CT b2;
+                a2[k] = inner4<T, CT>(bm2[k], bm1[k], Bf[V + k], bp1[k], idz_);
+            b1[k] = inner4<T, CT>(Bf[V + k - 2], Bf[V + k - 1], Bf[V + k], Bf[V + k + 1], idx_);
             if (EDGE && ft && J == 1) // odd mirror of σzz at the free surface (:85-93)
-                b2 = inner4<T, CT>(-zp1[k], z0v[k], zp1[k], zp2[k], idz_);
+                b2[k] = inner4<T, CT>(-zp1[k], z0v[k], zp1[k], zp2[k], idz_);
             else
-                b2 = inner4<T, CT>(zm1[k], z0v[k], zp1[k], zp2[k], idz_);
-            CT b1c = b1, b2c = b2;
-            if (EDGE && vz[k]) {
-                if (xs)
-                    b1c = cpml4<T, CT>(b1, I - 1, nx - 1, h, true, P.a_x, P.b_x, P.psi_in[1], P.psi_out[1], (long long)(J - 1) * (2 * (h + 1)), 1, true);
-                if (zs)
-                    b2c = cpml4<T, CT>(b2, J, nz, h, false, P.a_zh, P.b_zh, P.psi_in[2], P.psi_out[2], (long long)(I - 1), nx, true);
+                b2[k] = inner4<T, CT>(zm1[k], z0v[k], zp1[k], zp2[k], idz_);
+        }
+        if (EDGE) { // ∂̃: ψ_∂σxx∂x (0), ψ_∂σxz∂z (3) for ux; ψ_∂σxz∂x (1), ψ_∂σzz∂z (2) for uz
+            int ka[V], kb[V], oa[V], ob[V];
+            CpmlVec<T, V> ca, cb;
+            const int kz3 = zs ? cpml_k(J - 1, nz - 1, h, 1) : 0, kz2 = zs ? cpml_k(J, nz, h, 0) : 0;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int I = x0 + c0 + k + 1;
+                ka[k] = (xs && vx[k]) ? cpml_k(I, nx, h, 0) : 0;
+                oa[k] = (J - 1) * (2 * h) + (ka[k] - 1);
+                kb[k] = vx[k] ? kz3 : 0;
+                ob[k] = (I - 1) + (kz3 - 1) * (nx - 1);
             }
+            cpml_fetch<T, V>(ca, ka, oa, P.a_xh, P.b_xh, P.psi_in[0]);
+            cpml_fetch<T, V>(cb, kb, ob, P.a_z, P.b_z, P.psi_in[3]);
+            cpml_finish<T, CT, V>(a1, ca, ka, oa, vx, P.psi_out[0]);
+            cpml_finish<T, CT, V>(a2, cb, kb, ob, vx, P.psi_out[3]);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int I = x0 + c0 + k + 1;
+                ka[k] = (xs && vz[k]) ? cpml_k(I - 1, nx - 1, h, 1) : 0;
+                oa[k] = (J - 1) * (2 * (h + 1)) + (ka[k] - 1);
+                kb[k] = vz[k] ? kz2 : 0;
+                ob[k] = (I - 1) + (kz2 - 1) * nx;
+            }
+            cpml_fetch<T, V>(ca, ka, oa, P.a_x, P.b_x, P.psi_in[1]);
+            cpml_fetch<T, V>(cb, kb, ob, P.a_zh, P.b_zh, P.psi_in[2]);
+            cpml_finish<T, CT, V>(b1, ca, ka, oa, vz, P.psi_out[1]);
+            cpml_finish<T, CT, V>(b2, cb, kb, ob, vz, P.psi_out[2]);
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const T tx = fma((T)2, ucx[k], -r_uxo[n][k]); // = 2 ucur - uold rounded once (2 ucur is exact)
+            nx_[k] = (T)MAD(r_fi[n][k], a1[k] + a2[k], tx);
             const T tz = fma((T)2, ucz[k], -r_uzo[n][k]);
-            nz_[k] = (T)MAD(r_fj[n][k], b1c + b2c, tz);
+            nz_[k] = (T)MAD(r_fj[n][k], b1[k] + b2[k], tz);
         }
         if (!EDGE) {
             stv(P.uxn + q, nx_);
