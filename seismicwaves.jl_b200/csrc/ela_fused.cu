@@ -33,6 +33,7 @@
 #include "ela_fused.h"
 #include "kernels.h"
 #include <cstdlib>
+#include <type_traits>
 
 namespace swb {
 
@@ -267,6 +268,328 @@ __device__ __forceinline__ void inject_mt(const ElaFusedParams<T> &P, ElaSmem<T,
 // free-surface rows, so the reference's expressions reduce to the plain 4-point derivatives.  EDGE = true: the reference's
 // range tests, free-surface rows and ∂̃ memory variables per cell.  The two outermost vectors of a stress row (columns
 // -4 .. -1 and TX .. TX+3) hold two needed and two junk cells each; junk is computed from in-bounds shared memory and never read.
+// everything a vector task of the tile body needs
+template <class T, int TZ, bool ADJ>
+struct TileCtx {
+    const ElaFusedParams<T> &P;
+    ElaSmem<T, TZ, ADJ> &S;
+    int x0, z0, nx, nz, h, j0;
+    long long ld;
+    bool ft, xs, zs;
+    T idx_, idz_;
+};
+
+// phase 2, one vector of the stress region (row rr, vector column vv).  SP = false: the interior expressions; SP = true: range
+// tests, free-surface rows and ∂̃ per cell
+template <class T, class CT, int TZ, bool ADJ, bool SP>
+__device__ __forceinline__ void stress_task(const TileCtx<T, TZ, ADJ> &C, const int rr, const int vv)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int NV = W / V, NVT = TX / V;
+    const ElaFusedParams<T> &P = C.P;
+    ElaSmem<T, TZ, ADJ> &S = C.S;
+    const int x0 = C.x0, z0 = C.z0, nx = C.nx, nz = C.nz, h = C.h, j0 = C.j0;
+    const long long ld = C.ld;
+    const bool ft = C.ft, xs = C.xs, zs = C.zs;
+    const T idx_ = C.idx_, idz_ = C.idz_;
+    (void)NV, (void)NVT, (void)j0, (void)ld, (void)xs, (void)zs, (void)nx, (void)nz, (void)h, (void)ft;
+    const int r = rr - 2, c0 = vv * V - 4; // first cell of the vector
+    const int ou = (rr + 2) * W + vv * V;  // ... in ux / uz
+    const int os = rr * W + vv * V;        // ... in the stress / factor / forward-field arrays
+    const int J = z0 + r + 1;              // 1-based reference row
+    T X[3][V], Z[3][V], xm1[V], xp1[V], xp2[V], zm2[V], zm1[V], zp1[V], l[V], m[V], mh[V];
+    ldv(S.ux + ou - V, X[0]);
+    ldv(S.ux + ou, X[1]);
+    ldv(S.ux + ou + V, X[2]);
+    ldv(S.uz + ou - V, Z[0]);
+    ldv(S.uz + ou, Z[1]);
+    ldv(S.uz + ou + V, Z[2]);
+    ldv(S.ux + ou - W, xm1);
+    ldv(S.ux + ou + W, xp1);
+    ldv(S.ux + ou + 2 * W, xp2);
+    ldv(S.uz + ou - 2 * W, zm2);
+    ldv(S.uz + ou - W, zm1);
+    ldv(S.uz + ou + W, zp1);
+    ldv(S.sxx + os, l);
+    ldv(S.szz + os, m);
+    ldv(S.sxz + os, mh);
+    const T *Xf = &X[0][0], *Zf = &Z[0][0]; // columns c0 - V .. c0 + 2 V - 1 of row r
+    T oxx[V], ozz[V], oxz[V];
+    CT dudx[V], dwdz[V], dwdx[V], dudz[V]; // before ∂̃: the adjoint strains of the correlation
+    bool v1[V], v2[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int c = c0 + k, I = x0 + c + 1;
+        v1[k] = v2[k] = true;
+        if (SP) {
+            const bool inreg = c >= -2 && c <= TX + 1;
+            v1[k] = inreg && I >= 2 && I <= nx - 1 && J >= j0 && J <= nz - 1;
+            v2[k] = inreg && I >= 1 && I <= nx - 1 && J >= 1 && J <= nz - 1;
+        }
+        dudx[k] = inner4<T, CT>(Xf[V + k - 2], Xf[V + k - 1], Xf[V + k], Xf[V + k + 1], idx_);
+        if (SP && ft && J == 1) { // Hooke's law on the free-surface row (:179-195)
+            const T fac = -l[k] / (l[k] + (T)2 * m[k]);
+            dwdz[k] = (CT)fac * dudx[k];
+        } else
+            dwdz[k] = inner4<T, CT>((SP && ft && J == 2) ? zm1[k] : zm2[k], zm1[k], Zf[V + k], zp1[k], idz_);
+        dwdx[k] = inner4<T, CT>(Zf[V + k - 1], Zf[V + k], Zf[V + k + 1], Zf[V + k + 2], idx_);
+        // (even mirror of ux at the free surface, :214-222)
+        dudz[k] = inner4<T, CT>((SP && ft && J == 1) ? xp1[k] : xm1[k], Xf[V + k], xp1[k], xp2[k], idz_);
+    }
+    CT dudx_c[V], dwdz_c[V], dwdx_c[V], dudz_c[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+        dudx_c[k] = dudx[k], dwdz_c[k] = dwdz[k], dwdx_c[k] = dwdx[k], dudz_c[k] = dudz[k];
+    if (SP) { // ∂̃: ψ_∂ux∂x (4), ψ_∂uz∂z (7) for σxx, σzz; ψ_∂uz∂x (5), ψ_∂ux∂z (6) for σxz
+        int ka[V], kb[V], oa[V], ob[V];
+        bool st[V];
+        CpmlVec<T, V> ca, cb;
+        const int kz7 = zs ? cpml_k(J - 1, nz - 1, h, 1) : 0, kz6 = zs ? cpml_k(J, nz, h, 0) : 0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int c = c0 + k, I = x0 + c + 1;
+            st[k] = r >= 0 && r < TZ && c >= 0 && c < TX;
+            ka[k] = (xs && v1[k]) ? cpml_k(I - 1, nx - 1, h, 1) : 0;
+            oa[k] = (J - 1) * (2 * (h + 1)) + (ka[k] - 1);
+            kb[k] = v1[k] ? kz7 : 0;
+            ob[k] = (I - 1) + (kz7 - 1) * nx;
+        }
+        cpml_fetch<T, V>(ca, ka, oa, P.a_x, P.b_x, P.psi_in[4]);
+        cpml_fetch<T, V>(cb, kb, ob, P.a_z, P.b_z, P.psi_in[7]);
+        cpml_finish<T, CT, V>(dudx_c, ca, ka, oa, st, P.psi_out[4]);
+        cpml_finish<T, CT, V>(dwdz_c, cb, kb, ob, st, P.psi_out[7]);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int I = x0 + c0 + k + 1;
+            ka[k] = (xs && v2[k]) ? cpml_k(I, nx, h, 0) : 0;
+            oa[k] = (J - 1) * (2 * h) + (ka[k] - 1);
+            kb[k] = v2[k] ? kz6 : 0;
+            ob[k] = (I - 1) + (kz6 - 1) * (nx - 1);
+        }
+        cpml_fetch<T, V>(ca, ka, oa, P.a_xh, P.b_xh, P.psi_in[5]);
+        cpml_fetch<T, V>(cb, kb, ob, P.a_zh, P.b_zh, P.psi_in[6]);
+        cpml_finish<T, CT, V>(dwdx_c, ca, ka, oa, st, P.psi_out[5]);
+        cpml_finish<T, CT, V>(dudz_c, cb, kb, ob, st, P.psi_out[6]);
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const T l2m = l[k] + (T)2 * m[k];
+        oxx[k] = (T)MAD(l2m, dudx_c[k], (CT)l[k] * dwdz_c[k]);
+        ozz[k] = (SP && J == 1) ? (T)0 : (T)MAD(l[k], dudx_c[k], (CT)l2m * dwdz_c[k]);
+        oxz[k] = (T)((CT)mh[k] * (dwdx_c[k] + dudz_c[k]));
+        if (SP && !v1[k])
+            oxx[k] = ozz[k] = (T)0;
+        if (SP && !v2[k])
+            oxz[k] = (T)0;
+    }
+    stv(S.sxx + os, oxx);
+    stv(S.szz + os, ozz);
+    stv(S.sxz + os, oxz);
+    if (ADJ) { // grad_λ, grad_μ, grad_μ_ihalf_jhalf of the owned cells (correlate_gradient_xPU.jl:62-82)
+        if (r >= 0 && r < TZ && c0 >= 0 && c0 < TX) {
+            const long long q = (long long)(z0 + r) * ld + (x0 + c0);
+            T gl[V], gm[V], gh[V], F[3][V], G[3][V], fm1[V], fp1[V], fp2[V], gm2[V], gm1[V], gp1[V];
+            if (!SP) {
+                ldv(P.g_l + q, gl);
+                ldv(P.g_m + q, gm);
+                ldv(P.g_mh + q, gh);
+            }
+            ldv(S.fx + os - V, F[0]);
+            ldv(S.fx + os, F[1]);
+            ldv(S.fx + os + V, F[2]);
+            ldv(S.fz + os - V, G[0]);
+            ldv(S.fz + os, G[1]);
+            ldv(S.fz + os + V, G[2]);
+            ldv(S.fx + os - W, fm1);
+            ldv(S.fx + os + W, fp1);
+            ldv(S.fx + os + 2 * W, fp2);
+            ldv(S.fz + os - 2 * W, gm2);
+            ldv(S.fz + os - W, gm1);
+            ldv(S.fz + os + W, gp1);
+            const T *Ff = &F[0][0], *Gf = &G[0][0];
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int I = x0 + c0 + k + 1;
+                const bool surf = SP && ft && J == 1;
+                const bool w1 = !SP || (I >= 2 && I <= nx - 1 && J >= j0 && J <= nz - 1);
+                const bool w2 = !SP || (I <= nx - 1 && J <= nz - 1);
+                if (w1) {
+                    if (SP)
+                        gl[k] = P.g_l[q + k], gm[k] = P.g_m[q + k];
+                    const CT exx = inner4<T, CT>(Ff[V + k - 2], Ff[V + k - 1], Ff[V + k], Ff[V + k + 1], idx_);
+                    CT ezz;
+                    if (surf) {
+                        const T fac = -l[k] / (l[k] + (T)2 * m[k]);
+                        ezz = (CT)fac * exx;
+                    } else
+                        ezz = inner4<T, CT>((SP && ft && J == 2) ? gm1[k] : gm2[k], gm1[k], Gf[V + k], gp1[k], idz_);
+                    const CT exx_a = dudx[k], ezz_a = dwdz[k];
+                    const CT div_u = exx + ezz, div_a = exx_a + ezz_a;
+                    if (surf) {
+                        gl[k] = (T)((CT)gl[k] + (div_u * div_a) / (CT)2);
+                        gm[k] = (T)((CT)gm[k] + (exx * exx_a + ezz * ezz_a));
+                    } else {
+                        gl[k] = (T)((CT)gl[k] + div_u * div_a);
+                        gm[k] = (T)((CT)gm[k] + (CT)2 * (exx * exx_a + ezz * ezz_a));
+                    }
+                    if (SP)
+                        P.g_l[q + k] = gl[k], P.g_m[q + k] = gm[k];
+                }
+                if (w2) {
+                    if (SP)
+                        gh[k] = P.g_mh[q + k];
+                    const CT fdwdx = inner4<T, CT>(Gf[V + k - 1], Gf[V + k], Gf[V + k + 1], Gf[V + k + 2], idx_);
+                    const CT fdudz = inner4<T, CT>(surf ? fp1[k] : fm1[k], Ff[V + k], fp1[k], fp2[k], idz_);
+                    const CT exz = (fdwdx + fdudz) / (CT)2, exz_a = (dwdx[k] + dudz[k]) / (CT)2;
+                    gh[k] = (T)((CT)gh[k] + (CT)2 * (exz * exz_a + exz * exz_a));
+                    if (SP)
+                        P.g_mh[q + k] = gh[k];
+                }
+            }
+            if (!SP) {
+                stv(P.g_l + q, gl);
+                stv(P.g_m + q, gm);
+                stv(P.g_mh + q, gh);
+            }
+        }
+    }
+}
+
+// phase 3, one vector of the tile (row r, vector column v)
+template <class T, class CT, int TZ, bool ADJ, bool SP>
+__device__ __forceinline__ void disp_task(const TileCtx<T, TZ, ADJ> &C, const int r, const int v, const T (&uxo_)[16 / sizeof(T)], const T (&uzo_)[16 / sizeof(T)],
+                                          const T (&fi_)[16 / sizeof(T)], const T (&fj_)[16 / sizeof(T)])
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int NV = W / V, NVT = TX / V;
+    const ElaFusedParams<T> &P = C.P;
+    ElaSmem<T, TZ, ADJ> &S = C.S;
+    const int x0 = C.x0, z0 = C.z0, nx = C.nx, nz = C.nz, h = C.h, j0 = C.j0;
+    const long long ld = C.ld;
+    const bool ft = C.ft, xs = C.xs, zs = C.zs;
+    const T idx_ = C.idx_, idz_ = C.idz_;
+    (void)NV, (void)NVT, (void)j0, (void)ld, (void)xs, (void)zs, (void)nx, (void)nz, (void)h, (void)ft;
+    const int c0 = v * V;
+    const int J = z0 + r + 1;
+    const long long q = (long long)(z0 + r) * ld + (x0 + c0);
+    const int os = (r + 2) * W + c0 + 4;
+    T A[3][V], B[3][V], bm2[V], bm1[V], bp1[V], zm1[V], z0v[V], zp1[V], zp2[V], ucx[V], ucz[V];
+    ldv(S.sxx + os - V, A[0]);
+    ldv(S.sxx + os, A[1]);
+    ldv(S.sxx + os + V, A[2]);
+    ldv(S.sxz + os - V, B[0]);
+    ldv(S.sxz + os, B[1]);
+    ldv(S.sxz + os + V, B[2]);
+    ldv(S.sxz + os - 2 * W, bm2);
+    ldv(S.sxz + os - W, bm1);
+    ldv(S.sxz + os + W, bp1);
+    ldv(S.szz + os - W, zm1);
+    ldv(S.szz + os, z0v);
+    ldv(S.szz + os + W, zp1);
+    ldv(S.szz + os + 2 * W, zp2);
+    ldv(S.ux + os + 2 * W, ucx);
+    ldv(S.uz + os + 2 * W, ucz);
+    const T *Af = &A[0][0], *Bf = &B[0][0];
+    T nx_[V], nz_[V];
+    bool vx[V], vz[V];
+    CT a1[V], a2[V], b1[V], b2[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int I = x0 + c0 + k + 1;
+        vx[k] = !SP || (I <= nx - 1 && J <= nz);
+        vz[k] = !SP || (I <= nx && J <= nz - 1);
+        a1[k] = inner4<T, CT>(Af[V + k - 1], Af[V + k], Af[V + k + 1], Af[V + k + 2], idx_);
+        if (SP && ft && J == 1) // odd mirror of σxz at the free surface (:125-140)
+            a2[k] = inner4<T, CT>(-bp1[k], -Bf[V + k], Bf[V + k], bp1[k], idz_);
+        else if (SP && ft && J == 2)
+            a2[k] = inner4<T, CT>(-bm1[k], bm1[k], Bf[V + k], bp1[k], idz_);
+        else
+            a2[k] = inner4<T, CT>(bm2[k], bm1[k], Bf[V + k], bp1[k], idz_);
+        b1[k] = inner4<T, CT>(Bf[V + k - 2], Bf[V + k - 1], Bf[V + k], Bf[V + k + 1], idx_);
+        if (SP && ft && J == 1) // odd mirror of σzz at the free surface (:85-93)
+            b2[k] = inner4<T, CT>(-zp1[k], z0v[k], zp1[k], zp2[k], idz_);
+        else
+            b2[k] = inner4<T, CT>(zm1[k], z0v[k], zp1[k], zp2[k], idz_);
+    }
+    if (SP) { // ∂̃: ψ_∂σxx∂x (0), ψ_∂σxz∂z (3) for ux; ψ_∂σxz∂x (1), ψ_∂σzz∂z (2) for uz
+        int ka[V], kb[V], oa[V], ob[V];
+        CpmlVec<T, V> ca, cb;
+        const int kz3 = zs ? cpml_k(J - 1, nz - 1, h, 1) : 0, kz2 = zs ? cpml_k(J, nz, h, 0) : 0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int I = x0 + c0 + k + 1;
+            ka[k] = (xs && vx[k]) ? cpml_k(I, nx, h, 0) : 0;
+            oa[k] = (J - 1) * (2 * h) + (ka[k] - 1);
+            kb[k] = vx[k] ? kz3 : 0;
+            ob[k] = (I - 1) + (kz3 - 1) * (nx - 1);
+        }
+        cpml_fetch<T, V>(ca, ka, oa, P.a_xh, P.b_xh, P.psi_in[0]);
+        cpml_fetch<T, V>(cb, kb, ob, P.a_z, P.b_z, P.psi_in[3]);
+        cpml_finish<T, CT, V>(a1, ca, ka, oa, vx, P.psi_out[0]);
+        cpml_finish<T, CT, V>(a2, cb, kb, ob, vx, P.psi_out[3]);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int I = x0 + c0 + k + 1;
+            ka[k] = (xs && vz[k]) ? cpml_k(I - 1, nx - 1, h, 1) : 0;
+            oa[k] = (J - 1) * (2 * (h + 1)) + (ka[k] - 1);
+            kb[k] = vz[k] ? kz2 : 0;
+            ob[k] = (I - 1) + (kz2 - 1) * nx;
+        }
+        cpml_fetch<T, V>(ca, ka, oa, P.a_x, P.b_x, P.psi_in[1]);
+        cpml_fetch<T, V>(cb, kb, ob, P.a_zh, P.b_zh, P.psi_in[2]);
+        cpml_finish<T, CT, V>(b1, ca, ka, oa, vz, P.psi_out[1]);
+        cpml_finish<T, CT, V>(b2, cb, kb, ob, vz, P.psi_out[2]);
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const T tx = fma((T)2, ucx[k], -uxo_[k]); // = 2 ucur - uold rounded once (2 ucur is exact)
+        nx_[k] = (T)MAD(fi_[k], a1[k] + a2[k], tx);
+        const T tz = fma((T)2, ucz[k], -uzo_[k]);
+        nz_[k] = (T)MAD(fj_[k], b1[k] + b2[k], tz);
+    }
+    if (!SP) {
+        stv(P.uxn + q, nx_);
+        stv(P.uzn + q, nz_);
+    } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if (vx[k])
+                P.uxn[q + k] = nx_[k];
+            if (vz[k])
+                P.uzn[q + k] = nz_[k];
+        }
+    }
+    if (ADJ) { // grad_ρ_ihalf, grad_ρ_jhalf (correlate_gradient_xPU.jl:50-60), all in T
+        T fxo[V], fzo[V], fxn[V], fzn[V], gi[V], gj[V], fcx[V], fcz[V];
+        ldv_ro(P.fxo + q, fxo);
+        ldv_ro(P.fzo + q, fzo);
+        ldv_ro(P.fxn + q, fxn);
+        ldv_ro(P.fzn + q, fzn);
+        ldv(P.g_ri + q, gi);
+        ldv(P.g_rj + q, gj);
+        ldv(S.fx + os, fcx);
+        ldv(S.fz + os, fcz);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const T vi = (ucx[k] * ((fxo[k] - (T)2 * fcx[k]) + fxn[k])) * P.inv_dt2;
+            gi[k] = gi[k] + ((SP && ft && J == 1) ? vi / (T)2 : vi);
+            gj[k] = gj[k] + (ucz[k] * ((fzo[k] - (T)2 * fcz[k]) + fzn[k])) * P.inv_dt2;
+        }
+        if (!SP) {
+            stv(P.g_ri + q, gi);
+            stv(P.g_rj + q, gj);
+        } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                if (vx[k])
+                    P.g_ri[q + k] = gi[k];
+                if (vz[k])
+                    P.g_rj[q + k] = gj[k];
+            }
+        }
+    }
+}
+
 // Tile rows are issued bottom strip rows first, then from the top: the rows that touch the bottom C-PML strip run the slow
 // per-cell body and would otherwise form a tail of long CTAs at the end of the grid.
 template <int TZ>
@@ -330,296 +653,99 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
     __syncthreads(); // (the mbarrier's initialisation becomes visible to the waiting threads)
     mbar_wait(&S.bar, 0);
 
+    // Edge tiles split their vectors into plain ones (the interior expressions are exact: no strip, no edge, no free-surface row
+    // within the vector's needed cells) and special ones, enumerated compactly in a second pass, so that a C-PML column strip of
+    // a few vectors does not drag whole warps through the per-cell code.  plain cells: I in [Ilo, Ihi], J in [Jlo, Jhi].
+    const int Ilo = max(h + 2, 2), Ihi = nx - h - 2, Jlo = max(h + 2, 3), Jhi = nz - h - 2;
+    const TileCtx<T, TZ, ADJ> C{P, S, x0, z0, nx, nz, h, j0, ld, ft, xs, zs, idx_, idz_};
+
     // ---- phase 2: stresses on the tile + 2-cell halo (update_σxx_σzz! :39-60, update_σxz! :62-79) ------------------------
-    for (int t = tid; t < SH * NV; t += NTHR) {
-        const int rr = t / NV, vv = t - rr * NV;
-        const int r = rr - 2, c0 = vv * V - 4; // first cell of the vector
-        const int ou = (rr + 2) * W + vv * V;  // ... in ux / uz
-        const int os = rr * W + vv * V;        // ... in the stress / factor / forward-field arrays
-        const int J = z0 + r + 1;              // 1-based reference row
-        T X[3][V], Z[3][V], xm1[V], xp1[V], xp2[V], zm2[V], zm1[V], zp1[V], l[V], m[V], mh[V];
-        ldv(S.ux + ou - V, X[0]);
-        ldv(S.ux + ou, X[1]);
-        ldv(S.ux + ou + V, X[2]);
-        ldv(S.uz + ou - V, Z[0]);
-        ldv(S.uz + ou, Z[1]);
-        ldv(S.uz + ou + V, Z[2]);
-        ldv(S.ux + ou - W, xm1);
-        ldv(S.ux + ou + W, xp1);
-        ldv(S.ux + ou + 2 * W, xp2);
-        ldv(S.uz + ou - 2 * W, zm2);
-        ldv(S.uz + ou - W, zm1);
-        ldv(S.uz + ou + W, zp1);
-        ldv(S.sxx + os, l);
-        ldv(S.szz + os, m);
-        ldv(S.sxz + os, mh);
-        const T *Xf = &X[0][0], *Zf = &Z[0][0]; // columns c0 - V .. c0 + 2 V - 1 of row r
-        T oxx[V], ozz[V], oxz[V];
-        CT dudx[V], dwdz[V], dwdx[V], dudz[V]; // before ∂̃: the adjoint strains of the correlation
-        bool v1[V], v2[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-            const int c = c0 + k, I = x0 + c + 1;
-            v1[k] = v2[k] = true;
-            if (EDGE) {
-                const bool inreg = c >= -2 && c <= TX + 1;
-                v1[k] = inreg && I >= 2 && I <= nx - 1 && J >= j0 && J <= nz - 1;
-                v2[k] = inreg && I >= 1 && I <= nx - 1 && J >= 1 && J <= nz - 1;
-            }
-            dudx[k] = inner4<T, CT>(Xf[V + k - 2], Xf[V + k - 1], Xf[V + k], Xf[V + k + 1], idx_);
-            if (EDGE && ft && J == 1) { // Hooke's law on the free-surface row (:179-195)
-                const T fac = -l[k] / (l[k] + (T)2 * m[k]);
-                dwdz[k] = (CT)fac * dudx[k];
-            } else
-                dwdz[k] = inner4<T, CT>((EDGE && ft && J == 2) ? zm1[k] : zm2[k], zm1[k], Zf[V + k], zp1[k], idz_);
-            dwdx[k] = inner4<T, CT>(Zf[V + k - 1], Zf[V + k], Zf[V + k + 1], Zf[V + k + 2], idx_);
-            // (even mirror of ux at the free surface, :214-222)
-            dudz[k] = inner4<T, CT>((EDGE && ft && J == 1) ? xp1[k] : xm1[k], Xf[V + k], xp1[k], xp2[k], idz_);
+    if (!EDGE) {
+        for (int t = tid; t < SH * NV; t += NTHR) {
+            const int rr = t / NV;
+            stress_task<T, CT, TZ, ADJ, false>(C, rr, t - rr * NV);
         }
-        CT dudx_c[V], dwdz_c[V], dwdx_c[V], dudz_c[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k)
-            dudx_c[k] = dudx[k], dwdz_c[k] = dwdz[k], dwdx_c[k] = dwdx[k], dudz_c[k] = dudz[k];
-        if (EDGE) { // ∂̃: ψ_∂ux∂x (4), ψ_∂uz∂z (7) for σxx, σzz; ψ_∂uz∂x (5), ψ_∂ux∂z (6) for σxz
-            int ka[V], kb[V], oa[V], ob[V];
-            bool st[V];
-            CpmlVec<T, V> ca, cb;
-            const int kz7 = zs ? cpml_k(J - 1, nz - 1, h, 1) : 0, kz6 = zs ? cpml_k(J, nz, h, 0) : 0;
-#pragma unroll
-            for (int k = 0; k < V; ++k) {
-                const int c = c0 + k, I = x0 + c + 1;
-                st[k] = r >= 0 && r < TZ && c >= 0 && c < TX;
-                ka[k] = (xs && v1[k]) ? cpml_k(I - 1, nx - 1, h, 1) : 0;
-                oa[k] = (J - 1) * (2 * (h + 1)) + (ka[k] - 1);
-                kb[k] = v1[k] ? kz7 : 0;
-                ob[k] = (I - 1) + (kz7 - 1) * nx;
-            }
-            cpml_fetch<T, V>(ca, ka, oa, P.a_x, P.b_x, P.psi_in[4]);
-            cpml_fetch<T, V>(cb, kb, ob, P.a_z, P.b_z, P.psi_in[7]);
-            cpml_finish<T, CT, V>(dudx_c, ca, ka, oa, st, P.psi_out[4]);
-            cpml_finish<T, CT, V>(dwdz_c, cb, kb, ob, st, P.psi_out[7]);
-#pragma unroll
-            for (int k = 0; k < V; ++k) {
-                const int I = x0 + c0 + k + 1;
-                ka[k] = (xs && v2[k]) ? cpml_k(I, nx, h, 0) : 0;
-                oa[k] = (J - 1) * (2 * h) + (ka[k] - 1);
-                kb[k] = v2[k] ? kz6 : 0;
-                ob[k] = (I - 1) + (kz6 - 1) * (nx - 1);
-            }
-            cpml_fetch<T, V>(ca, ka, oa, P.a_xh, P.b_xh, P.psi_in[5]);
-            cpml_fetch<T, V>(cb, kb, ob, P.a_zh, P.b_zh, P.psi_in[6]);
-            cpml_finish<T, CT, V>(dwdx_c, ca, ka, oa, st, P.psi_out[5]);
-            cpml_finish<T, CT, V>(dudz_c, cb, kb, ob, st, P.psi_out[6]);
+    } else {
+        // special rows [0, za) and [zb, SH), special vector columns [0, xa) and [xb, NV) of the stress region
+        const int za = min(max(Jlo - (z0 - 1), 0), SH), zb = min(max(Jhi - (z0 - 1) + 1, za), SH);
+        int xa = 0, xb = NV;
+        for (int vv = 0; vv < NV; ++vv) {
+            const int lo_c = max(V * vv - 4, -2), hi_c = min(V * vv - 4 + V - 1, TX + 1);
+            if (x0 + lo_c + 1 < Ilo)
+                xa = vv + 1;
+            if (x0 + hi_c + 1 > Ihi && xb == NV)
+                xb = vv;
         }
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-            const T l2m = l[k] + (T)2 * m[k];
-            oxx[k] = (T)MAD(l2m, dudx_c[k], (CT)l[k] * dwdz_c[k]);
-            ozz[k] = (EDGE && J == 1) ? (T)0 : (T)MAD(l[k], dudx_c[k], (CT)l2m * dwdz_c[k]);
-            oxz[k] = (T)((CT)mh[k] * (dwdx_c[k] + dudz_c[k]));
-            if (EDGE && !v1[k])
-                oxx[k] = ozz[k] = (T)0;
-            if (EDGE && !v2[k])
-                oxz[k] = (T)0;
+        xb = max(xb, xa);
+        for (int t = tid; t < SH * NV; t += NTHR) {
+            const int rr = t / NV, vv = t - rr * NV;
+            if (rr >= za && rr < zb && vv >= xa && vv < xb)
+                stress_task<T, CT, TZ, ADJ, false>(C, rr, vv);
         }
-        stv(S.sxx + os, oxx);
-        stv(S.szz + os, ozz);
-        stv(S.sxz + os, oxz);
-        if (ADJ) { // grad_λ, grad_μ, grad_μ_ihalf_jhalf of the owned cells (correlate_gradient_xPU.jl:62-82)
-            if (r >= 0 && r < TZ && c0 >= 0 && c0 < TX) {
-                const long long q = (long long)(z0 + r) * ld + (x0 + c0);
-                T gl[V], gm[V], gh[V], F[3][V], G[3][V], fm1[V], fp1[V], fp2[V], gm2[V], gm1[V], gp1[V];
-                if (!EDGE) {
-                    ldv(P.g_l + q, gl);
-                    ldv(P.g_m + q, gm);
-                    ldv(P.g_mh + q, gh);
-                }
-                ldv(S.fx + os - V, F[0]);
-                ldv(S.fx + os, F[1]);
-                ldv(S.fx + os + V, F[2]);
-                ldv(S.fz + os - V, G[0]);
-                ldv(S.fz + os, G[1]);
-                ldv(S.fz + os + V, G[2]);
-                ldv(S.fx + os - W, fm1);
-                ldv(S.fx + os + W, fp1);
-                ldv(S.fx + os + 2 * W, fp2);
-                ldv(S.fz + os - 2 * W, gm2);
-                ldv(S.fz + os - W, gm1);
-                ldv(S.fz + os + W, gp1);
-                const T *Ff = &F[0][0], *Gf = &G[0][0];
-#pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    const int I = x0 + c0 + k + 1;
-                    const bool surf = EDGE && ft && J == 1;
-                    const bool w1 = !EDGE || (I >= 2 && I <= nx - 1 && J >= j0 && J <= nz - 1);
-                    const bool w2 = !EDGE || (I <= nx - 1 && J <= nz - 1);
-                    if (w1) {
-                        if (EDGE)
-                            gl[k] = P.g_l[q + k], gm[k] = P.g_m[q + k];
-                        const CT exx = inner4<T, CT>(Ff[V + k - 2], Ff[V + k - 1], Ff[V + k], Ff[V + k + 1], idx_);
-                        CT ezz;
-                        if (surf) {
-                            const T fac = -l[k] / (l[k] + (T)2 * m[k]);
-                            ezz = (CT)fac * exx;
-                        } else
-                            ezz = inner4<T, CT>((EDGE && ft && J == 2) ? gm1[k] : gm2[k], gm1[k], Gf[V + k], gp1[k], idz_);
-                        const CT exx_a = dudx[k], ezz_a = dwdz[k];
-                        const CT div_u = exx + ezz, div_a = exx_a + ezz_a;
-                        if (surf) {
-                            gl[k] = (T)((CT)gl[k] + (div_u * div_a) / (CT)2);
-                            gm[k] = (T)((CT)gm[k] + (exx * exx_a + ezz * ezz_a));
-                        } else {
-                            gl[k] = (T)((CT)gl[k] + div_u * div_a);
-                            gm[k] = (T)((CT)gm[k] + (CT)2 * (exx * exx_a + ezz * ezz_a));
-                        }
-                        if (EDGE)
-                            P.g_l[q + k] = gl[k], P.g_m[q + k] = gm[k];
-                    }
-                    if (w2) {
-                        if (EDGE)
-                            gh[k] = P.g_mh[q + k];
-                        const CT fdwdx = inner4<T, CT>(Gf[V + k - 1], Gf[V + k], Gf[V + k + 1], Gf[V + k + 2], idx_);
-                        const CT fdudz = inner4<T, CT>(surf ? fp1[k] : fm1[k], Ff[V + k], fp1[k], fp2[k], idz_);
-                        const CT exz = (fdwdx + fdudz) / (CT)2, exz_a = (dwdx[k] + dudz[k]) / (CT)2;
-                        gh[k] = (T)((CT)gh[k] + (CT)2 * (exz * exz_a + exz * exz_a));
-                        if (EDGE)
-                            P.g_mh[q + k] = gh[k];
-                    }
-                }
-                if (!EDGE) {
-                    stv(P.g_l + q, gl);
-                    stv(P.g_m + q, gm);
-                    stv(P.g_mh + q, gh);
-                }
+        const int nzs = za + (SH - zb), nxs = xa + (NV - xb);
+        const int n1 = nzs * NV, n2 = (SH - nzs) * nxs;
+        for (int t = tid; t < n1 + n2; t += NTHR) {
+            int rr, vv;
+            if (t < n1) {
+                const int i = t / NV;
+                vv = t - i * NV;
+                rr = i < za ? i : zb + (i - za);
+            } else {
+                const int t2 = t - n1, i = t2 / nxs, jx = t2 - i * nxs;
+                rr = za + i;
+                vv = jx < xa ? jx : xb + (jx - xa);
             }
+            stress_task<T, CT, TZ, ADJ, true>(C, rr, vv);
         }
     }
     __syncthreads();
     inject_mt<T, TZ, ADJ>(P, S, tile, tid);
 
     // ---- phase 3: displacements of the tile (update_ux! :1-18, update_uz! :20-37) -----------------------------------------
+    if (!EDGE) {
 #pragma unroll
-    for (int n = 0; n < NP3; ++n) {
-        const int t = tid + NTHR * n;
-        const int r = t / NVT, v = t - r * NVT;
-        const int c0 = v * V;
-        const int J = z0 + r + 1;
-        const long long q = (long long)(z0 + r) * ld + (x0 + c0);
-        const int os = (r + 2) * W + c0 + 4;
-        T A[3][V], B[3][V], bm2[V], bm1[V], bp1[V], zm1[V], z0v[V], zp1[V], zp2[V], ucx[V], ucz[V];
-        ldv(S.sxx + os - V, A[0]);
-        ldv(S.sxx + os, A[1]);
-        ldv(S.sxx + os + V, A[2]);
-        ldv(S.sxz + os - V, B[0]);
-        ldv(S.sxz + os, B[1]);
-        ldv(S.sxz + os + V, B[2]);
-        ldv(S.sxz + os - 2 * W, bm2);
-        ldv(S.sxz + os - W, bm1);
-        ldv(S.sxz + os + W, bp1);
-        ldv(S.szz + os - W, zm1);
-        ldv(S.szz + os, z0v);
-        ldv(S.szz + os + W, zp1);
-        ldv(S.szz + os + 2 * W, zp2);
-        ldv(S.ux + os + 2 * W, ucx);
-        ldv(S.uz + os + 2 * W, ucz);
-        const T *Af = &A[0][0], *Bf = &B[0][0];
-        T nx_[V], nz_[V];
-        bool vx[V], vz[V];
-        CT a1[V], a2[V], b1[V], b2[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-            const int I = x0 + c0 + k + 1;
-            vx[k] = !EDGE || (I <= nx - 1 && J <= nz);
-            vz[k] = !EDGE || (I <= nx && J <= nz - 1);
-            a1[k] = inner4<T, CT>(Af[V + k - 1], Af[V + k], Af[V + k + 1], Af[V + k + 2], idx_);
-            if (EDGE && ft && J == 1) // odd mirror of σxz at the free surface (:125-140)
-                a2[k] = inner4<T, CT>(-bp1[k], -Bf[V + k], Bf[V + k], bp1[k], idz_);
-            else if (EDGE && ft && J == 2)
-                a2[k] = inner4<T, CT>(-bm1[k], bm1[k], Bf[V + k], bp1[k], idz_);
-            else
-                a2[k] = inner4<T, CT>(bm2[k], bm1[k], Bf[V + k], bp1[k], idz_);
-            b1[k] = inner4<T, CT>(Bf[V + k - 2], Bf[V + k - 1], Bf[V + k], Bf[V + k + 1], idx_);
-            if (EDGE && ft && J == 1) // odd mirror of σzz at the free surface (:85-93)
-                b2[k] = inner4<T, CT>(-zp1[k], z0v[k], zp1[k], zp2[k], idz_);
-            else
-                b2[k] = inner4<T, CT>(zm1[k], z0v[k], zp1[k], zp2[k], idz_);
+        for (int n = 0; n < NP3; ++n) {
+            const int t = tid + NTHR * n;
+            const int r = t / NVT;
+            disp_task<T, CT, TZ, ADJ, false>(C, r, t - r * NVT, r_uxo[n], r_uzo[n], r_fi[n], r_fj[n]);
         }
-        if (EDGE) { // ∂̃: ψ_∂σxx∂x (0), ψ_∂σxz∂z (3) for ux; ψ_∂σxz∂x (1), ψ_∂σzz∂z (2) for uz
-            int ka[V], kb[V], oa[V], ob[V];
-            CpmlVec<T, V> ca, cb;
-            const int kz3 = zs ? cpml_k(J - 1, nz - 1, h, 1) : 0, kz2 = zs ? cpml_k(J, nz, h, 0) : 0;
-#pragma unroll
-            for (int k = 0; k < V; ++k) {
-                const int I = x0 + c0 + k + 1;
-                ka[k] = (xs && vx[k]) ? cpml_k(I, nx, h, 0) : 0;
-                oa[k] = (J - 1) * (2 * h) + (ka[k] - 1);
-                kb[k] = vx[k] ? kz3 : 0;
-                ob[k] = (I - 1) + (kz3 - 1) * (nx - 1);
-            }
-            cpml_fetch<T, V>(ca, ka, oa, P.a_xh, P.b_xh, P.psi_in[0]);
-            cpml_fetch<T, V>(cb, kb, ob, P.a_z, P.b_z, P.psi_in[3]);
-            cpml_finish<T, CT, V>(a1, ca, ka, oa, vx, P.psi_out[0]);
-            cpml_finish<T, CT, V>(a2, cb, kb, ob, vx, P.psi_out[3]);
-#pragma unroll
-            for (int k = 0; k < V; ++k) {
-                const int I = x0 + c0 + k + 1;
-                ka[k] = (xs && vz[k]) ? cpml_k(I - 1, nx - 1, h, 1) : 0;
-                oa[k] = (J - 1) * (2 * (h + 1)) + (ka[k] - 1);
-                kb[k] = vz[k] ? kz2 : 0;
-                ob[k] = (I - 1) + (kz2 - 1) * nx;
-            }
-            cpml_fetch<T, V>(ca, ka, oa, P.a_x, P.b_x, P.psi_in[1]);
-            cpml_fetch<T, V>(cb, kb, ob, P.a_zh, P.b_zh, P.psi_in[2]);
-            cpml_finish<T, CT, V>(b1, ca, ka, oa, vz, P.psi_out[1]);
-            cpml_finish<T, CT, V>(b2, cb, kb, ob, vz, P.psi_out[2]);
+    } else {
+        const int za = min(max(Jlo - (z0 + 1), 0), TZ), zb = min(max(Jhi - (z0 + 1) + 1, za), TZ);
+        int xa = 0, xb = NVT;
+        for (int v = 0; v < NVT; ++v) {
+            if (x0 + V * v + 1 < Ilo)
+                xa = v + 1;
+            if (x0 + V * v + V > Ihi && xb == NVT)
+                xb = v;
         }
+        xb = max(xb, xa);
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-            const T tx = fma((T)2, ucx[k], -r_uxo[n][k]); // = 2 ucur - uold rounded once (2 ucur is exact)
-            nx_[k] = (T)MAD(r_fi[n][k], a1[k] + a2[k], tx);
-            const T tz = fma((T)2, ucz[k], -r_uzo[n][k]);
-            nz_[k] = (T)MAD(r_fj[n][k], b1[k] + b2[k], tz);
+        for (int n = 0; n < NP3; ++n) {
+            const int t = tid + NTHR * n;
+            const int r = t / NVT, v = t - r * NVT;
+            if (r >= za && r < zb && v >= xa && v < xb)
+                disp_task<T, CT, TZ, ADJ, false>(C, r, v, r_uxo[n], r_uzo[n], r_fi[n], r_fj[n]);
         }
-        if (!EDGE) {
-            stv(P.uxn + q, nx_);
-            stv(P.uzn + q, nz_);
-        } else {
-#pragma unroll
-            for (int k = 0; k < V; ++k) {
-                if (vx[k])
-                    P.uxn[q + k] = nx_[k];
-                if (vz[k])
-                    P.uzn[q + k] = nz_[k];
-            }
-        }
-        if (ADJ) { // grad_ρ_ihalf, grad_ρ_jhalf (correlate_gradient_xPU.jl:50-60), all in T
-            T fxo[V], fzo[V], fxn[V], fzn[V], gi[V], gj[V], fcx[V], fcz[V];
-            ldv_ro(P.fxo + q, fxo);
-            ldv_ro(P.fzo + q, fzo);
-            ldv_ro(P.fxn + q, fxn);
-            ldv_ro(P.fzn + q, fzn);
-            ldv(P.g_ri + q, gi);
-            ldv(P.g_rj + q, gj);
-            ldv(S.fx + os, fcx);
-            ldv(S.fz + os, fcz);
-#pragma unroll
-            for (int k = 0; k < V; ++k) {
-                const T vi = (ucx[k] * ((fxo[k] - (T)2 * fcx[k]) + fxn[k])) * P.inv_dt2;
-                gi[k] = gi[k] + ((EDGE && ft && J == 1) ? vi / (T)2 : vi);
-                gj[k] = gj[k] + (ucz[k] * ((fzo[k] - (T)2 * fcz[k]) + fzn[k])) * P.inv_dt2;
-            }
-            if (!EDGE) {
-                stv(P.g_ri + q, gi);
-                stv(P.g_rj + q, gj);
+        const int nzs = za + (TZ - zb), nxs = xa + (NVT - xb);
+        const int n1 = nzs * NVT, n2 = (TZ - nzs) * nxs;
+        for (int t = tid; t < n1 + n2; t += NTHR) {
+            int r, v;
+            if (t < n1) {
+                const int i = t / NVT;
+                v = t - i * NVT;
+                r = i < za ? i : zb + (i - za);
             } else {
-#pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    if (vx[k])
-                        P.g_ri[q + k] = gi[k];
-                    if (vz[k])
-                        P.g_rj[q + k] = gj[k];
-                }
+                const int t2 = t - n1, i = t2 / nxs, jx = t2 - i * nxs;
+                r = za + i;
+                v = jx < xa ? jx : xb + (jx - xa);
             }
+            const long long q = (long long)(z0 + r) * ld + (x0 + v * V);
+            T uxo_[V], uzo_[V], fi_[V], fj_[V]; // (the owner of these cells has not written them yet: they are written here)
+            ldv(P.uxo + q, uxo_);
+            ldv(P.uzo + q, uzo_);
+            ldv_ro(P.fac_ih + q, fi_);
+            ldv_ro(P.fac_jh + q, fj_);
+            disp_task<T, CT, TZ, ADJ, true>(C, r, v, uxo_, uzo_, fi_, fj_);
         }
     }
 
