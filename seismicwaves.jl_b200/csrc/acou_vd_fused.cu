@@ -108,6 +108,17 @@ __device__ __forceinline__ void stage_rows(T *dst, int dstride, const T *src_row
     }
 }
 
+// Tile rows are issued bottom strip rows first, then from the top: the rows that touch the bottom C-PML strip run the slow
+// generic body and would otherwise form a tail of long CTAs at the end of the grid.
+template <int TY>
+__device__ __forceinline__ int vd_tile_row(int halo)
+{
+    const int nty = (int)gridDim.y;
+    const int nedge = min(nty, (halo + 6 + TY + TY - 1) / TY);
+    const int by = (int)blockIdx.y + nty - nedge;
+    return by >= nty ? by - nty : by;
+}
+
 template <class T, class CT, bool ADJ, int TY, bool edge>
 __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char *smem_raw)
 {
@@ -118,10 +129,11 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
     T *svy = sm + L::VY_OFF, *sm1y = sm + L::M1Y_OFF, *spi = sm + L::PI_OFF + SW + 8;
 
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int trow = vd_tile_row<TY>(P.halo);
+    const int x0 = blockIdx.x * TX, y0 = trow * TY;
     const int nx = P.nx, ny = P.ny, h = P.halo;
     const long long ld = P.ld;
-    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int tile = trow * gridDim.x + blockIdx.x;
 
     // ---- phase 1: stage every input of the tile in shared memory ------------------------------------------
     {
@@ -355,9 +367,10 @@ __device__ __forceinline__ void vd_tile_interior(const VdFusedParams<T> &P, unsi
     T *svy = sm + L::VY_OFF, *sm1y = sm + L::M1Y_OFF, *spi = sm + L::PI_OFF + SW + 8;
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int trow = vd_tile_row<TY>(P.halo);
+    const int x0 = blockIdx.x * TX, y0 = trow * TY;
     const long long ld = P.ld;
-    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int tile = trow * gridDim.x + blockIdx.x;
     const long long o = (long long)y0 * ld + x0 + 4 * lane; // this lane's chunk in row 0 of the tile
     // lanes 0..3 additionally fetch the halo chunks -2, -1, NCH, NCH+1 of a row
     const int hc = lane < 2 ? lane - 2 - lane : NCH + (lane - 2) - lane; // chunk offset relative to this lane's own chunk
@@ -546,7 +559,7 @@ template <class T, class CT, bool ADJ, int TY>
 __global__ void __launch_bounds__(NTHR, sizeof(T) == 4 ? (ADJ ? 3 : 4) : 1) vd_fused_kernel(const VdFusedParams<T> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, h = P.halo;
+    const int x0 = blockIdx.x * TX, y0 = vd_tile_row<TY>(P.halo) * TY, h = P.halo;
     // block-uniform: does the tile (with the halo it recomputes) touch a C-PML strip or the grid edge?
     const bool edge = (x0 - 8 <= h + 2) || (x0 + TX + 8 >= P.nx - h - 2) || (y0 - 4 <= h + 2) || (y0 + TY + 4 >= P.ny - h - 2);
     if (edge)
