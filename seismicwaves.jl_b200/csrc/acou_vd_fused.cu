@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "vd_fused.h"
+#include <cstdlib>
 
 namespace swb {
 
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(NTHR, sizeof(T) == 4 ? (ADJ ? 3 : 4) : 1) vd_f
     const int x0 = blockIdx.x * TX, y0 = vd_tile_row<TY>(P.halo) * TY, h = P.halo;
     // block-uniform: does the tile (with the halo it recomputes) touch a C-PML strip or the grid edge?
     const bool edge = (x0 - 8 <= h + 2) || (x0 + TX + 8 >= P.nx - h - 2) || (y0 - 4 <= h + 2) || (y0 + TY + 4 >= P.ny - h - 2);
-    if (edge)
+    if (edge && !P.dbg_all_interior)
         vd_tile<T, CT, ADJ, TY, true>(P, smem_raw);
     else
         vd_tile_interior<T, CT, ADJ, TY>(P, smem_raw);
@@ -588,9 +589,12 @@ void launch_one(const VdFusedParams<T> &P, cudaStream_t st)
 } // namespace
 
 template <class T>
-void vd_fused_launch(const VdFusedParams<T> &P, bool fast, cudaStream_t st)
+void vd_fused_launch(const VdFusedParams<T> &P0, bool fast, cudaStream_t st)
 {
     constexpr int TY = VDF_TY;
+    static const int dbg = [] { const char *e = std::getenv("SWB_VD_DEBUG_ALL_INTERIOR"); return e ? std::atoi(e) : 0; }();
+    VdFusedParams<T> P = P0;
+    P.dbg_all_interior = dbg;
     if (sizeof(T) == 8 || !fast) {
         if (P.adj)
             launch_one<T, double, true, TY>(P, st);

@@ -300,6 +300,16 @@ __device__ __forceinline__ void stress_task(const TileCtx<T, TZ, ADJ> &C, const 
     const int ou = (rr + 2) * W + vv * V;  // ... in ux / uz
     const int os = rr * W + vv * V;        // ... in the stress / factor / forward-field arrays
     const int J = z0 + r + 1;              // 1-based reference row
+    if (SP && (J < 1 || J > nz - 1)) {     // outside every update range: zero stresses
+        T zero_[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            zero_[k] = (T)0;
+        stv(S.sxx + os, zero_);
+        stv(S.szz + os, zero_);
+        stv(S.sxz + os, zero_);
+        return;
+    }
     T X[3][V], Z[3][V], xm1[V], xp1[V], xp2[V], zm2[V], zm1[V], zp1[V], l[V], m[V], mh[V];
     ldv(S.ux + ou - V, X[0]);
     ldv(S.ux + ou, X[1]);
@@ -474,6 +484,8 @@ __device__ __forceinline__ void disp_task(const TileCtx<T, TZ, ADJ> &C, const in
     (void)NV, (void)NVT, (void)j0, (void)ld, (void)xs, (void)zs, (void)nx, (void)nz, (void)h, (void)ft;
     const int c0 = v * V;
     const int J = z0 + r + 1;
+    if (SP && J > nz)
+        return; // below the grid
     const long long q = (long long)(z0 + r) * ld + (x0 + c0);
     const int os = (r + 2) * W + c0 + 4;
     T A[3][V], B[3][V], bm2[V], bm1[V], bp1[V], zm1[V], z0v[V], zp1[V], zp2[V], ucx[V], ucz[V];
@@ -625,7 +637,7 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
     // does the tile's stress region reach an x / a z strip (or edge)?  ∂̃ is the identity elsewhere (CTA-uniform tests)
     const int mm = max(h + 1, 2);
     const bool xs = EDGE && !(x0 - 1 > mm && x0 + TX + 2 < nx - 1 - h);
-    const bool zs = EDGE && !(z0 - 1 > mm && z0 + TZ + 2 < nz - 1 - h);
+    const bool zs = EDGE && !((P.top_inactive || z0 - 1 > mm) && z0 + TZ + 2 < nz - 1 - h);
 
     // ---- phase 1: one thread requests the shared-memory working set (TMA), all threads their owned uold and dt²/ρ ----------
     if (tid == 0) {
@@ -659,7 +671,7 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
     // Edge tiles split their vectors into plain ones (the interior expressions are exact: no strip, no edge, no free-surface row
     // within the vector's needed cells) and special ones, enumerated compactly in a second pass, so that a C-PML column strip of
     // a few vectors does not drag whole warps through the per-cell code.  plain cells: I in [Ilo, Ihi], J in [Jlo, Jhi].
-    const int Ilo = max(h + 2, 2), Ihi = nx - h - 2, Jlo = max(h + 2, 3), Jhi = nz - h - 2;
+    const int Ilo = max(h + 2, 2), Ihi = nx - h - 2, Jlo = P.top_inactive ? 3 : max(h + 2, 3), Jhi = nz - h - 2;
     const TileCtx<T, TZ, ADJ> C{P, S, x0, z0, nx, nz, h, j0, ld, ft, xs, zs, idx_, idz_};
 
     // ---- phase 2: stresses on the tile + 2-cell halo (update_σxx_σzz! :39-60, update_σxz! :62-79) ------------------------
@@ -793,8 +805,8 @@ __global__ void __launch_bounds__(NTHR, 2) ela_fused_kernel(const __grid_constan
     // interior tile: every cell of the tile's stress region (1-based indices x0-1 .. x0+TX+2, z0-1 .. z0+TZ+2) lies inside all
     // update ranges, outside every C-PML strip and below the free-surface rows
     const int m = max(P.halo + 1, 2);
-    const bool interior = x0 - 1 > m && x0 + TX + 2 < P.nx - 1 - P.halo && z0 - 1 > m && z0 + TZ + 2 < P.nz - 1 - P.halo;
-    if (interior)
+    const bool interior = x0 - 1 > m && x0 + TX + 2 < P.nx - 1 - P.halo && z0 - 1 > (P.top_inactive ? 2 : m) && z0 + TZ + 2 < P.nz - 1 - P.halo;
+    if (interior || P.dbg_all_interior)
         ela_tile<T, CT, TZ, ADJ, false>(P, S);
     else
         ela_tile<T, CT, TZ, ADJ, true>(P, S);
@@ -915,8 +927,11 @@ __global__ void __launch_bounds__(256) elf_dt2_over_rho_kernel(long long ld, lon
 } // namespace
 
 template <class T, class CT, int TZ, bool ADJ>
-static void ela_fused_launch_v(const ElaFusedParams<T> &P, cudaStream_t st)
+static void ela_fused_launch_v(const ElaFusedParams<T> &P0, cudaStream_t st)
 {
+    static const int dbg = [] { const char *e = std::getenv("SWB_ELF_DEBUG_ALL_INTERIOR"); return e ? std::atoi(e) : 0; }();
+    ElaFusedParams<T> P = P0;
+    P.dbg_all_interior = dbg;
     const dim3 grd(cdiv(P.nx, TX), cdiv(P.nz, TZ), 1);
     const size_t smem = sizeof(ElaSmem<T, TZ, ADJ>);
     int dev = 0;

@@ -25,6 +25,7 @@ struct ElaFusedParams {
     // TMA descriptors of the padded planes staged through shared memory: ux, uz (current), λ, μ, μ_ihalf_jhalf, forward ux, uz [it-1]
     alignas(64) CUtensorMap tm[7];
     int nx, nz, halo, freetop, tz;
+    int top_inactive; // the top C-PML strip has a = 0 (free surface): its memory variables stay 0 and ∂̃ = ∂ there
     long long ld;
     T inv_dx, inv_dz, dt;
     // padded planes, pointers to cell (1,1) of each array (ux: (nx-1, nz), uz: (nx, nz-1), ...)
@@ -58,6 +59,7 @@ struct ElaFusedParams {
     const T *fxo, *fzo, *fxc, *fzc, *fxn, *fzn; // forward u[it-2], u[it-1], u[it]
     T *g_ri, *g_rj, *g_l, *g_m, *g_mh;
     T inv_dt2;
+    int dbg_all_interior; // timing experiment only (SWB_ELF_DEBUG_ALL_INTERIOR=1): wrong results in the strips
 };
 
 template <class T>

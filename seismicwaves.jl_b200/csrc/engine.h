@@ -159,6 +159,8 @@ class SimBase {
 
     DevBuf cpml_[3][4]; // a, a_h, b, b_h per axis
     bool cpml_set_[3] = {false, false, false};
+    // the lower strip of an axis has a = a_h = 0 (free-surface override of init_bdc!, acou_init_bc.jl:33-39): its memory variables stay 0
+    bool cpml_lo_inactive_[3] = {false, false, false};
     // acoustic shot binding
     DevBuf possrc_, posrec_, srctf_, traces_, adjsrc_;
     int64_t nsrc_ = 0, nrec_ = 0;

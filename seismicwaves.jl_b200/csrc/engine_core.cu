@@ -327,6 +327,16 @@ void SimBase::set_cpml(int axis, const void *a, const void *a_h, const void *b, 
     upload(cpml_[axis][1].p, a_h, cpml_[axis][1].bytes);
     upload(cpml_[axis][2].p, b, cpml_[axis][2].bytes);
     upload(cpml_[axis][3].p, b_h, cpml_[axis][3].bytes);
+    {
+        auto lower_half_zero = [&](const void *v, size_t bytes) {
+            const size_t n = bytes / esize / 2;
+            for (size_t k = 0; k < n; ++k)
+                if ((esize == 8 ? ((const double *)v)[k] : (double)((const float *)v)[k]) != 0.0)
+                    return false;
+            return true;
+        };
+        cpml_lo_inactive_[axis] = lower_half_zero(a, cpml_[axis][0].bytes) && lower_half_zero(a_h, cpml_[axis][1].bytes);
+    }
     cpml_set_[axis] = true;
 }
 

@@ -42,6 +42,7 @@ struct VdFusedParams {
     // adjoint-mode correlation
     const T *pc_it, *pc_itm1;
     T *g0, *g1x, *g1y;
+    int dbg_all_interior; // timing experiment only (SWB_VD_DEBUG_ALL_INTERIOR=1): wrong results in the strips
 };
 
 template <class T>
