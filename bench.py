@@ -351,6 +351,8 @@ def run_b200(args):
     if args.grid == 4096 and args.nt == 1000:
         assert float(np.abs(grad["vp"]).max()) > 0, "gradient is empty"
 
+    dominant_kernel, device_bytes = wavesim.dominant_kernel_name(), wavesim.device_bytes()
+    wavesim.close()
     if rank == 0:
         peaks = {}
         try:
@@ -366,7 +368,7 @@ def run_b200(args):
         if kt_n > 0:
             dur = kt_ms / kt_n * 1e-3
             ach = bytes_per_cell * n * n / dur / 1e9
-            roof = {"bound": "hbm", "kernel": wavesim.dominant_kernel_name(), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            roof = {"bound": "hbm", "kernel": dominant_kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": 585.0e6 if (args.grid == 4096 and args.fast_f32) else None,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one forward launch, ncu --set full (profiles/r1_ncu_vd_fwd3_fast.txt)",
                     "peak_source": peak_src, "frac_of_8TBs_nominal": ach / 8000.0, "avg_launch_us": dur * 1e6, "timed_launches": kt_n,
@@ -387,8 +389,10 @@ def run_b200(args):
             "clocks": clocks, "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "seconds": float(te.item())},
             "gpu_launches": int(launches), "roofline": roof, "misfit_last_shot": float(misfit_val.value),
             "useful_Gcell_per_s": 2.0 * n * n * nt * args.steps * world / (ms_max * 1e-3) / 1e9,
-            "device_bytes": wavesim.device_bytes(),
+            "device_bytes": device_bytes,
         }
+        if world == 1 and not args.no_extras and args.grid == 4096 and args.nt == 1000:
+            line["other_configs"] = other_configs(peak)
         if not args.no_cpu:
             cores = os.cpu_count() or 1
             os.environ.setdefault("OMP_NUM_THREADS", str(cores))
@@ -405,9 +409,33 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if comm is not None:
         lib.swb_comm_destroy(comm)
-    wavesim.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(peak):
+    """Per-launch timings of the other fused engines on the BASELINE.json configurations that are not the headline (C3 elastic at
+    full size, 2D / 3D constant-density at sizes that take seconds): CUDA events over whole replayed sweeps, a few dozen steps
+    each (tools/bench_sim.py).  Informational: `value` above is C2 only."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_sim
+
+    runs = [("C3 elastic P-SV 4096x2048 Float32 (f32 arithmetic)", "--kind ela --n 4096 2048 --nt 60 --check-freq 10 --dtype f32 --fast-f32 1 --nrec 10 --reps 2"),
+            ("C3 elastic P-SV 4096x2048 Float64", "--kind ela --n 4096 2048 --nt 60 --check-freq 10 --dtype f64 --nrec 10 --reps 2"),
+            ("2D acoustic CD 4096x4096 Float32 (C1 physics at roofline size)", "--kind cd --n 4096 4096 --nt 100 --check-freq 10 --reps 2"),
+            ("C4-like 3D acoustic CD 512^3 Float32 (768^3 needs 155 GB of checkpoints: profiles/r1_cd_c4_fullsize.log)", "--kind cd --n 512 512 512 --nt 30 --check-freq 10 --reps 2")]
+    out = []
+    for name, argv in runs:
+        try:
+            r = bench_sim.measure(bench_sim.parse_args(argv.split()))
+            rec = {"config": name, "device_GB": r["device_GB"]}
+            for k in ("fwd", "adj"):
+                if k in r:
+                    rec[k] = {"us_per_step": r[k]["us"], "Gcell_per_s": r[k]["Gcell_s"], "algorithmic_GBps": r[k]["GBps"], "frac_of_peak": r[k]["GBps"] / peak}
+            out.append(rec)
+        except Exception as e:  # noqa: BLE001 -- the headline line must survive a failing extra
+            out.append({"config": name, "error": str(e)[:200]})
+    return out
 
 
 def main():
@@ -423,6 +451,7 @@ def main():
                     help="1 (default) = Float32 storage and Float32 arithmetic (SWB_FLAG_FAST_F32; within the 1e-4 Float32 tolerance); "
                          "0 = Float64 intermediates, bit-faithful to the reference's promotion rule")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-launch timings of the non-headline configurations (other_configs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -188,19 +188,30 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
                 const Chunk<T> ia = ldg_chunk(pis - 4), ib = ldg_chunk(pis), ic = ldg_chunk(pis + 4);
                 wi[0] = ia.v[3], wi[1] = ib.v[0], wi[2] = ib.v[1], wi[3] = ib.v[2], wi[4] = ib.v[3], wi[5] = ic.v[0], wi[6] = ic.v[1];
             }
+            // C-PML values of the chunk's cells are fetched together before use (one dependent global load per cell otherwise)
+            T ca[4], cb[4], cs[4];
+            int cq[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int I = gx + e + 1, J = gy + 1;
+                const bool in = edge && (I >= 1 && I <= nx - 1 && J <= ny) && (I <= h || I >= nx - h);
+                const int ii = I <= h ? I : I - nx + 2 * h + 1;
+                cq[e] = in ? (J - 1) * (2 * h) + (ii - 1) : -1;
+                ca[e] = in ? P.a_xh[ii - 1] : (T)0;
+                cb[e] = in ? P.b_xh[ii - 1] : (T)0;
+                cs[e] = in ? P.psi_x_in[cq[e]] : (T)0;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int I = gx + e + 1, J = gy + 1; // 1-based reference indices
                 if (edge && !(I >= 1 && I <= nx - 1 && J <= ny))
                     continue; // outside update_vx_CPML!'s range: stays as it is (zero)
                 CT D = fd4<T, CT>(P, w[e], w[e + 1], w[e + 2], w[e + 3], P.inv_dx);
-                if (edge && (I <= h || I >= nx - h)) {
-                    const int ii = I <= h ? I : I - nx + 2 * h + 1;
-                    const size_t qs = (size_t)(J - 1) * (2 * h) + (ii - 1);
+                if (edge && cq[e] >= 0) {
                     T sn;
-                    D = cpml_apply<T, CT>(D, P.a_xh[ii - 1], P.b_xh[ii - 1], P.psi_x_in[qs], sn);
+                    D = cpml_apply<T, CT>(D, ca[e], cb[e], cs[e], sn);
                     if (owned)
-                        P.psi_x_out[qs] = sn;
+                        P.psi_x_out[cq[e]] = sn;
                 }
                 out.v[e] = (T)((CT)vin.v[e] - (CT)m1.v[e] * D);
                 if (ADJ && owned) {
@@ -236,19 +247,35 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
                 const T *pis = spi + r * SW + 4 * c;
                 ia = ldg_chunk(pis - SW), ib = ldg_chunk(pis), ic = ldg_chunk(pis + SW), id = ldg_chunk(pis + 2 * SW);
             }
+            T ca = (T)0, cb = (T)0, cs[4];
+            int cq[4];
+            {
+                const int J = gy + 1;
+                const bool rowin = edge && J >= 1 && J <= ny - 1 && (J <= h || J >= ny - h);
+                const int jj = J <= h ? J : J - ny + 2 * h + 1;
+                if (rowin) {
+                    ca = P.a_yh[jj - 1];
+                    cb = P.b_yh[jj - 1];
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int I = gx + e + 1;
+                    const bool in = rowin && I <= nx;
+                    cq[e] = in ? (jj - 1) * nx + (I - 1) : -1;
+                    cs[e] = in ? P.psi_y_in[cq[e]] : (T)0;
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int I = gx + e + 1, J = gy + 1;
                 if (edge && !(I <= nx && J >= 1 && J <= ny - 1))
                     continue;
                 CT D = fd4<T, CT>(P, pa.v[e], pb.v[e], pc.v[e], pd.v[e], P.inv_dy);
-                if (edge && (J <= h || J >= ny - h)) {
-                    const int jj = J <= h ? J : J - ny + 2 * h + 1;
-                    const size_t qs = (size_t)(jj - 1) * nx + (I - 1);
+                if (edge && cq[e] >= 0) {
                     T sn;
-                    D = cpml_apply<T, CT>(D, P.a_yh[jj - 1], P.b_yh[jj - 1], P.psi_y_in[qs], sn);
+                    D = cpml_apply<T, CT>(D, ca, cb, cs[e], sn);
                     if (owned)
-                        P.psi_y_out[qs] = sn;
+                        P.psi_y_out[cq[e]] = sn;
                 }
                 out.v[e] = (T)((CT)vin.v[e] - (CT)m1.v[e] * D);
                 if (ADJ && owned) {
@@ -289,6 +316,32 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
         const Chunk<T> ya = ldg_chunk(vys - 2 * TX), yb = ldg_chunk(vys - TX), yc = ldg_chunk(vys), yd = ldg_chunk(vys + TX);
         const Chunk<T> pin = ldg_chunk(sp + r * SW + 4 * c);
         Chunk<T> out = pin;
+        T xa_[4], xb_[4], xs_[4], ya_ = (T)0, yb_ = (T)0, ys_[4];
+        int xq[4], yq[4];
+        {
+            const int J = gy + 1;
+            const bool rowok = edge && J >= 2 && J <= ny - 1;
+            const bool rowin = rowok && (J <= h + 1 || J >= ny - h);
+            const int jj = J <= h + 1 ? J : J - ny + 2 * h + 2;
+            if (rowin) {
+                ya_ = P.a_y[jj - 1];
+                yb_ = P.b_y[jj - 1];
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int I = gx + e + 1;
+                const bool ok = rowok && I >= 2 && I <= nx - 1;
+                const bool inx = ok && (I <= h + 1 || I >= nx - h);
+                const int ii = I <= h + 1 ? I : I - nx + 2 * h + 2;
+                xq[e] = inx ? (J - 1) * (2 * (h + 1)) + (ii - 1) : -1;
+                xa_[e] = inx ? P.a_x[ii - 1] : (T)0;
+                xb_[e] = inx ? P.b_x[ii - 1] : (T)0;
+                xs_[e] = inx ? P.xi_x_in[xq[e]] : (T)0;
+                const bool iny = ok && rowin;
+                yq[e] = iny ? (jj - 1) * nx + (I - 1) : -1;
+                ys_[e] = iny ? P.xi_y_in[yq[e]] : (T)0;
+            }
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int I = gx + e + 1, J = gy + 1;
@@ -296,20 +349,16 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
                 continue; // update_p_CPML! touches interior cells only
             // d vx / dx at I-1 (backward staggered): vx[I-2 .. I+1]
             CT Dx = fd4<T, CT>(P, wx[e], wx[e + 1], wx[e + 2], wx[e + 3], P.inv_dx);
-            if (edge && (I <= h + 1 || I >= nx - h)) {
-                const int ii = I <= h + 1 ? I : I - nx + 2 * h + 2;
-                const size_t qs = (size_t)(J - 1) * (2 * (h + 1)) + (ii - 1);
+            if (edge && xq[e] >= 0) {
                 T sn;
-                Dx = cpml_apply<T, CT>(Dx, P.a_x[ii - 1], P.b_x[ii - 1], P.xi_x_in[qs], sn);
-                P.xi_x_out[qs] = sn;
+                Dx = cpml_apply<T, CT>(Dx, xa_[e], xb_[e], xs_[e], sn);
+                P.xi_x_out[xq[e]] = sn;
             }
             CT Dy = fd4<T, CT>(P, ya.v[e], yb.v[e], yc.v[e], yd.v[e], P.inv_dy);
-            if (edge && (J <= h + 1 || J >= ny - h)) {
-                const int jj = J <= h + 1 ? J : J - ny + 2 * h + 2;
-                const size_t qs = (size_t)(jj - 1) * nx + (I - 1);
+            if (edge && yq[e] >= 0) {
                 T sn;
-                Dy = cpml_apply<T, CT>(Dy, P.a_y[jj - 1], P.b_y[jj - 1], P.xi_y_in[qs], sn);
-                P.xi_y_out[qs] = sn;
+                Dy = cpml_apply<T, CT>(Dy, ya_, yb_, ys_[e], sn);
+                P.xi_y_out[yq[e]] = sn;
             }
             out.v[e] = (T)((CT)pin.v[e] - (CT)m0.v[e] * (Dx + Dy));
         }

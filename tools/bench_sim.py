@@ -20,6 +20,11 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    args = parse_args()
+    print(json.dumps(measure(args)), flush=True)
+
+
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--kind", default="cd", choices=["cd", "vd", "ela"])
     ap.add_argument("--n", type=int, nargs="+", default=[768, 768, 768])
@@ -32,8 +37,11 @@ def main():
     ap.add_argument("--no-grad", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--nrec", type=int, default=64)
-    args = ap.parse_args()
+    return ap.parse_args(argv)
 
+
+def measure(args):
+    """run the configuration `args` describes (see parse_args) and return the timing record"""
     import swb200 as S
 
     S._lib.require_device()
@@ -110,8 +118,8 @@ def main():
         if a_n:
             da = (a_ms - r_n * (f_ms / f_n)) / a_n * 1e-3
             out["adj"] = {"us": da * 1e6, "GBps": bytes_adj * ncell / da / 1e9, "Gcell_s": ncell / da / 1e9, "launches": a_n, "refwd_launches": r_n}
-    print(json.dumps(out), flush=True)
     ws.close()
+    return out
 
 
 if __name__ == "__main__":
