@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "vd_fused.h"
+#include "tma.cuh"
 #include <cstdlib>
 
 namespace swb {
@@ -38,7 +39,7 @@ namespace {
 constexpr int TX = VDF_TX;        // tile width (cells)
 constexpr int NCH = TX / 4;       // 16-byte (float) / 32-byte (double) chunks per tile row
 constexpr int NTHR = 256;
-constexpr int SW = TX + 16;       // shared row width: columns -8 .. TX+7
+constexpr int SW = VDF_SW;        // shared row width: columns -8 .. TX+7
 
 template <class T>
 struct alignas(16) Chunk {
@@ -91,7 +92,43 @@ struct VdSmem {
     static constexpr int M1Y_OFF = VY_OFF + (TY + 3) * TX;       // m1y    same shape
     static constexpr int PI_OFF = M1Y_OFF + (TY + 3) * TX;       // p_it   rows -1 .. TY+1, cols -8 .. TX+7 (adjoint only)
     static constexpr int TOTAL = PI_OFF + (ADJ ? (TY + 3) * SW : 0);
+    static constexpr int BAR_OFF = TOTAL; // mbarrier of the TMA staging (8 bytes)
+    static constexpr size_t BYTES = sizeof(T) * (size_t)TOTAL + 16;
 };
+
+// phase 1 of both tile bodies: the elected thread arms the mbarrier and requests every staged array of the tile as one TMA box
+// (zeros outside the padded planes); the caller waits on the barrier after its own register loads.
+template <class T, int TY, bool ADJ>
+__device__ __forceinline__ void vd_stage_tma(const VdFusedParams<T> &P, T *sm, int x0, int y0)
+{
+    typedef VdSmem<T, TY, ADJ> L;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + L::BAR_OFF);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        unsigned bytes = (unsigned)(((TY + 6) * SW + TY * SW + (TY + 3) * TX) * sizeof(T));
+        if (P.do_v)
+            bytes += (unsigned)((TY * SW + (TY + 3) * TX) * sizeof(T));
+        if (ADJ)
+            bytes += (unsigned)((TY + 3) * SW * sizeof(T));
+        mbar_expect_tx(bar, bytes);
+        const int gb = PAD_GUARD_BEFORE;
+        tma_load_2d(sm + L::P_OFF, &P.tm[0], x0 - 8, gb + y0 - 3, bar);
+        tma_load_2d(sm + L::VX_OFF, &P.tm[1], x0 - 8, gb + y0, bar);
+        tma_load_2d(sm + L::VY_OFF, &P.tm[3], x0, gb + y0 - 2, bar);
+        if (P.do_v) {
+            tma_load_2d(sm + L::M1X_OFF, &P.tm[2], x0 - 8, gb + y0, bar);
+            tma_load_2d(sm + L::M1Y_OFF, &P.tm[4], x0, gb + y0 - 2, bar);
+        }
+        if (ADJ)
+            tma_load_2d(sm + L::PI_OFF, &P.tm[5], x0 - 8, gb + y0 - 1, bar);
+    }
+}
+template <class T, int TY, bool ADJ>
+__device__ __forceinline__ void vd_stage_wait(T *sm)
+{
+    __syncthreads(); // (the mbarrier's initialisation becomes visible to the waiting threads)
+    mbar_wait(reinterpret_cast<unsigned long long *>(sm + VdSmem<T, TY, ADJ>::BAR_OFF), 0);
+}
 
 // stage `nrows` rows of chunks [c0, c1) (chunk 0 = global column gx0) from a padded plane into shared memory
 template <class T>
@@ -136,24 +173,9 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
     const long long ld = P.ld;
     const int tile = trow * gridDim.x + blockIdx.x;
 
-    // ---- phase 1: stage every input of the tile in shared memory ------------------------------------------
-    {
-        const long long o = (long long)y0 * ld + x0;
-        // p_in: rows 0 .. TY-1 need columns -8 .. TX+7, the 3 halo rows above and below only columns 0 .. TX-1
-        stage_rows(sp, SW, P.p_in + o, ld, x0, TY, -2, NCH + 2, tid);
-        stage_rows(sp - 3 * SW, SW, P.p_in + o - 3 * ld, ld, x0, 3, 0, NCH, tid);
-        stage_rows(sp + TY * SW, SW, P.p_in + o + TY * ld, ld, x0, 3, 0, NCH, tid);
-        stage_rows(svx, SW, P.vx_in + o, ld, x0, TY, -1, NCH + 1, tid);
-        stage_rows(svy, TX, P.vy_in + o - 2 * ld, ld, x0, TY + 3, 0, NCH, tid);
-        if (P.do_v) {
-            stage_rows(sm1x, SW, P.m1x + o, ld, x0, TY, -1, NCH + 1, tid);
-            stage_rows(sm1y, TX, P.m1y + o - 2 * ld, ld, x0, TY + 3, 0, NCH, tid);
-        }
-        if (ADJ)
-            stage_rows(spi - SW, SW, P.pc_it + o - ld, ld, x0, TY + 3, -1, NCH + 1, tid);
-        cp_async_wait_all();
-        __syncthreads();
-    }
+    // ---- phase 1: stage every input of the tile in shared memory (TMA) ---------------------------------------
+    vd_stage_tma<T, TY, ADJ>(P, sm, x0, y0);
+    vd_stage_wait<T, TY, ADJ>(sm);
 
     // record_receivers!: traces[it, r] = p_in[rec]  (p_in is the pressure after the reference's step `rec_it`)
     if (P.rec_it > 0) {
@@ -425,56 +447,15 @@ __device__ __forceinline__ void vd_tile_interior(const VdFusedParams<T> &P, unsi
     // lanes 0..3 additionally fetch the halo chunks -2, -1, NCH, NCH+1 of a row
     const int hc = lane < 2 ? lane - 2 - lane : NCH + (lane - 2) - lane; // chunk offset relative to this lane's own chunk
 
-    // ---- phase 1: everything the tile needs goes into shared memory with cp.async ----------------------
-#pragma unroll
-    for (int k = 0; k < (TY + 6 + NW - 1) / NW; ++k) { // p_in rows -3 .. TY+2
-        const int r = w + NW * k - 3;
-        if (r < TY + 3) {
-            cp_async_chunk(sp + r * SW + 4 * lane, P.p_in + o + (long long)r * ld);
-            if (lane < 4 && r >= 0 && r < TY)
-                cp_async_chunk(sp + r * SW + 4 * (lane + hc), P.p_in + o + (long long)r * ld + 4 * hc);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < TY / NW; ++k) { // vx, m1x, m0 rows 0 .. TY-1 (vx / m1x with halo chunks -1 and NCH)
-        const int r = w + NW * k;
-        cp_async_chunk(svx + r * SW + 4 * lane, P.vx_in + o + (long long)r * ld);
-        if (P.do_v)
-            cp_async_chunk(sm1x + r * SW + 4 * lane, P.m1x + o + (long long)r * ld);
-        if (lane == 1 || lane == 2) {
-            cp_async_chunk(svx + r * SW + 4 * (lane + hc), P.vx_in + o + (long long)r * ld + 4 * hc);
-            if (P.do_v)
-                cp_async_chunk(sm1x + r * SW + 4 * (lane + hc), P.m1x + o + (long long)r * ld + 4 * hc);
-        }
-    }
-    Chunk<T> m0r[TY / NW]; // m0 is used once per cell: straight to registers, in flight together with the cp.async traffic
+    // ---- phase 1: everything the tile needs goes into shared memory (TMA), m0 straight to registers ---------
+    vd_stage_tma<T, TY, ADJ>(P, sm, x0, y0);
+    Chunk<T> m0r[TY / NW]; // m0 is used once per cell: in flight together with the TMA traffic
     if (P.do_p) {
 #pragma unroll
         for (int k = 0; k < TY / NW; ++k)
             m0r[k] = ldg_chunk(P.m0 + o + (long long)(w + NW * k) * ld);
     }
-#pragma unroll
-    for (int k = 0; k < (TY + 3 + NW - 1) / NW; ++k) { // vy, m1y rows -2 .. TY
-        const int rr = w + NW * k;
-        if (rr < TY + 3) {
-            cp_async_chunk(svy + rr * TX + 4 * lane, P.vy_in + o + (long long)(rr - 2) * ld);
-            if (P.do_v)
-                cp_async_chunk(sm1y + rr * TX + 4 * lane, P.m1y + o + (long long)(rr - 2) * ld);
-        }
-    }
-    if (ADJ) {
-#pragma unroll
-        for (int k = 0; k < (TY + 3 + NW - 1) / NW; ++k) { // p_it rows -1 .. TY+1, chunks -1 .. NCH
-            const int r = w + NW * k - 1;
-            if (r < TY + 2) {
-                cp_async_chunk(spi + r * SW + 4 * lane, P.pc_it + o + (long long)r * ld);
-                if (lane == 1 || lane == 2)
-                    cp_async_chunk(spi + r * SW + 4 * (lane + hc), P.pc_it + o + (long long)r * ld + 4 * hc);
-            }
-        }
-    }
-    cp_async_wait_all();
-    __syncthreads();
+    vd_stage_wait<T, TY, ADJ>(sm);
 
     if (P.rec_it > 0) { // record_receivers!
         const int e0 = P.rec_off[tile], e1 = P.rec_off[tile + 1];
@@ -606,9 +587,9 @@ __device__ __forceinline__ void vd_tile_interior(const VdFusedParams<T> &P, unsi
 }
 
 template <class T, class CT, bool ADJ, int TY>
-__global__ void __launch_bounds__(NTHR, sizeof(T) == 4 ? (ADJ ? 3 : 4) : 1) vd_fused_kernel(const VdFusedParams<T> P)
+__global__ void __launch_bounds__(NTHR, sizeof(T) == 4 ? (ADJ ? 3 : 4) : 1) vd_fused_kernel(const __grid_constant__ VdFusedParams<T> P)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int x0 = blockIdx.x * TX, y0 = vd_tile_row<TY>(P.halo) * TY, h = P.halo;
     // block-uniform: does the tile (with the halo it recomputes) touch a C-PML strip or the grid edge?
     const bool edge = (x0 - 8 <= h + 2) || (x0 + TX + 8 >= P.nx - h - 2) || (y0 - 4 <= h + 2) || (y0 + TY + 4 >= P.ny - h - 2);
@@ -621,7 +602,7 @@ __global__ void __launch_bounds__(NTHR, sizeof(T) == 4 ? (ADJ ? 3 : 4) : 1) vd_f
 template <class T, class CT, bool ADJ, int TY>
 void launch_one(const VdFusedParams<T> &P, cudaStream_t st)
 {
-    const size_t smem = sizeof(T) * (size_t)VdSmem<T, TY, ADJ>::TOTAL;
+    const size_t smem = VdSmem<T, TY, ADJ>::BYTES;
     auto kern = vd_fused_kernel<T, CT, ADJ, TY>;
     static bool configured = false; // per instantiation
     if (!configured) {

@@ -31,6 +31,7 @@
 // External-force / adjoint-source injection and the receiver sums stay separate small launches (elf_inject_force,
 // elf_record); elf_correlate is the stand-alone correlation (last adjoint step, step-by-step path).
 #include "ela_fused.h"
+#include "tma.cuh"
 #include "kernels.h"
 #include <cstdlib>
 #include <type_traits>
@@ -55,62 +56,13 @@ int elf_tz(int dtype, bool adjoint)
 // 2D tensor map of a whole padded plane (all guard rows included), box = ELF_SW columns x box_rows rows
 void elf_make_tmap(CUtensorMap *out, int dtype, const void *plane_base, long long ld, long long rows, int box_rows)
 {
-    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static encode_fn encode = [] {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        SWB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
-            throw Error(SWB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-        return (encode_fn)fn;
-    }();
-    const size_t es = dtype == SWB_F64 ? 8 : 4;
-    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
-    const cuuint64_t gstr[1] = {(cuuint64_t)ld * es};
-    const cuuint32_t box[2] = {(cuuint32_t)ELF_SW, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(out, dtype == SWB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(plane_base), gdim, gstr, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-        throw Error(SWB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    make_tmap_2d(out, dtype, plane_base, ld, rows, ELF_SW, box_rows);
 }
 
 namespace {
 
 constexpr int TX = ELF_TX, NTHR = 256;
 constexpr int W = ELF_SW; // row pitch of every staged array: columns -4 .. TX+3
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    asm volatile("{\n"
-                 ".reg .pred P1;\n"
-                 "LAB_WAIT:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-                 "@P1 bra DONE;\n"
-                 "bra LAB_WAIT;\n"
-                 "DONE:\n"
-                 "}\n" ::"r"(smem_u32(bar)),
-                 "r"(parity)
-                 : "memory");
-}
-// one TMA box: columns c0 .. c0 + ELF_SW - 1, rows c1 .. c1 + box_rows - 1 of a padded plane (zeros outside the plane)
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(smem_u32(dst)), "l"(map), "r"(c0),
-                 "r"(c1), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 // 16-byte vectors of consecutive cells
 __device__ __forceinline__ void ldv(const float *p, float (&o)[4])

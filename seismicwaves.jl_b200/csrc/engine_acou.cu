@@ -8,6 +8,7 @@
 #include "engine.h"
 #include "vd_fused.h"
 #include "cd_fused.h"
+#include "tma.cuh"
 #include <cstring>
 
 namespace swb {

@@ -5,7 +5,32 @@
 #include <cstring>
 #include <cmath>
 
+#include "tma.cuh"
 namespace swb {
+
+void make_tmap_2d(CUtensorMap *out, int dtype, const void *base, long long ld, long long rows, int box_w, int box_h)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SWB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
+            throw Error(SWB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        return (encode_fn)fn;
+    }();
+    const size_t es = dtype == SWB_F64 ? 8 : 4;
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld * es};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, dtype == SWB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        throw Error(SWB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+}
+
 
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_device_bytes{0};

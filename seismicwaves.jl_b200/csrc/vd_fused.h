@@ -1,6 +1,7 @@
 // vd_fused.h -- parameter block and layout constants of the fused 2D variable-density step (acou_vd_fused.cu).
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
 
 namespace swb {
 
@@ -14,8 +15,13 @@ inline long long padded_ld(long long nx) { return ((nx + 4 + 31) / 32) * 32; }
 inline size_t padded_plane_elems(long long nx, long long ny) { return (size_t)padded_ld(nx) * (size_t)(ny + PAD_GUARD_BEFORE + PAD_GUARD_AFTER); }
 inline size_t padded_origin(long long nx) { return (size_t)padded_ld(nx) * PAD_GUARD_BEFORE; }
 
+constexpr int VDF_SW = VDF_TX + 16; // staged row width of p, vx, m1x, p_it: columns -8 .. TX+7
+
 template <class T>
 struct VdFusedParams {
+    // TMA descriptors of the padded planes staged through shared memory (whole plane incl. guard rows; boxes: p_in VDF_SW x (TY+6),
+    // vx_in / m1x VDF_SW x TY, vy_in / m1y VDF_TX x (TY+3), pc_it VDF_SW x (TY+3))
+    alignas(64) CUtensorMap tm[6];
     int nx, ny, halo;
     long long ld;
     int do_v, do_p, adj;
