@@ -146,6 +146,247 @@ __device__ __forceinline__ void stage_rows(T *dst, int dstride, const T *src_row
     }
 }
 
+// ---- chunk bodies of the edge tiles.  SPC = true: the reference's range tests and C-PML per cell; SPC = false: the chunk lies
+//      inside every update range and outside every strip (plain expressions).  vd_tile runs the plain chunks in place and
+//      enumerates the special ones compactly in a second pass, so that a strip a few chunks wide does not drag whole warps
+//      through the per-cell code.
+template <class T>
+struct VdCtx {
+    const VdFusedParams<T> &P;
+    T *sp, *svx, *sm1x, *svy, *sm1y, *spi;
+    int x0, y0, nx, ny, h;
+    long long ld;
+};
+
+// vx_new of chunk column c (-1 .. NCH) of tile row r
+template <class T, class CT, bool ADJ, int TY, bool SPC>
+__device__ __forceinline__ void vd_edge_vx(const VdCtx<T> &C, const int r, const int c)
+{
+    const VdFusedParams<T> &P = C.P;
+    T *const sp = C.sp, *const svx = C.svx, *const sm1x = C.sm1x, *const svy = C.svy, *const sm1y = C.sm1y, *const spi = C.spi;
+    const int x0 = C.x0, y0 = C.y0, nx = C.nx, ny = C.ny, h = C.h;
+    const long long ld = C.ld;
+    (void)sp, (void)svx, (void)sm1x, (void)svy, (void)sm1y, (void)spi, (void)nx, (void)ny, (void)h;
+    const int gx = x0 + 4 * c, gy = y0 + r; // 0-based global column of the chunk's first cell / row
+    if (gx >= ld)
+        return;
+    const long long q = (long long)gy * ld + gx;
+    T *vs = svx + r * SW + 4 * c;
+    const Chunk<T> vin = ldg_chunk(vs);
+    const Chunk<T> m1 = ldg_chunk(sm1x + r * SW + 4 * c);
+    const T *ps = sp + r * SW + 4 * c; // p at column 4c
+    const Chunk<T> pa = ldg_chunk(ps - 4), pb = ldg_chunk(ps), pc = ldg_chunk(ps + 4);
+    const T w[7] = {pa.v[3], pb.v[0], pb.v[1], pb.v[2], pb.v[3], pc.v[0], pc.v[1]};
+    const bool owned = c >= 0 && c < NCH && gy < ny;
+    Chunk<T> out = vin, g1 = {};
+    T wi[7];
+    if (ADJ && owned) {
+        g1 = ldg_chunk(P.g1x + q);
+        const T *pis = spi + r * SW + 4 * c;
+        const Chunk<T> ia = ldg_chunk(pis - 4), ib = ldg_chunk(pis), ic = ldg_chunk(pis + 4);
+        wi[0] = ia.v[3], wi[1] = ib.v[0], wi[2] = ib.v[1], wi[3] = ib.v[2], wi[4] = ib.v[3], wi[5] = ic.v[0], wi[6] = ic.v[1];
+    }
+    // C-PML values of the chunk's cells are fetched together before use (one dependent global load per cell otherwise)
+    T ca[4], cb[4], cs[4];
+    int cq[4];
+    #pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int I = gx + e + 1, J = gy + 1;
+        const bool in = SPC && (I >= 1 && I <= nx - 1 && J <= ny) && (I <= h || I >= nx - h);
+        const int ii = I <= h ? I : I - nx + 2 * h + 1;
+        cq[e] = in ? (J - 1) * (2 * h) + (ii - 1) : -1;
+        ca[e] = in ? P.a_xh[ii - 1] : (T)0;
+        cb[e] = in ? P.b_xh[ii - 1] : (T)0;
+        cs[e] = in ? P.psi_x_in[cq[e]] : (T)0;
+    }
+    #pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int I = gx + e + 1, J = gy + 1; // 1-based reference indices
+        if (SPC && !(I >= 1 && I <= nx - 1 && J <= ny))
+            continue; // outside update_vx_CPML!'s range: stays as it is (zero)
+        CT D = fd4<T, CT>(P, w[e], w[e + 1], w[e + 2], w[e + 3], P.inv_dx);
+        if (SPC && cq[e] >= 0) {
+            T sn;
+            D = cpml_apply<T, CT>(D, ca[e], cb[e], cs[e], sn);
+            if (owned)
+                P.psi_x_out[cq[e]] = sn;
+        }
+        out.v[e] = (T)((CT)vin.v[e] - (CT)m1.v[e] * D);
+        if (ADJ && owned) {
+            const CT Dc = fd4<T, CT>(P, wi[e], wi[e + 1], wi[e + 2], wi[e + 3], P.inv_dx);
+            g1.v[e] = (T)((CT)g1.v[e] + (CT)out.v[e] * Dc);
+        }
+    }
+    st_chunk(vs, out);
+    if (owned) {
+        st_chunk(P.vx_out + q, out);
+        if (ADJ)
+            st_chunk(P.g1x + q, g1);
+    }
+}
+
+// vy_new of chunk column c of staged row rr (tile row rr - 2)
+template <class T, class CT, bool ADJ, int TY, bool SPC>
+__device__ __forceinline__ void vd_edge_vy(const VdCtx<T> &C, const int rr, const int c)
+{
+    const VdFusedParams<T> &P = C.P;
+    T *const sp = C.sp, *const svx = C.svx, *const sm1x = C.sm1x, *const svy = C.svy, *const sm1y = C.sm1y, *const spi = C.spi;
+    const int x0 = C.x0, y0 = C.y0, nx = C.nx, ny = C.ny, h = C.h;
+    const long long ld = C.ld;
+    (void)sp, (void)svx, (void)sm1x, (void)svy, (void)sm1y, (void)spi, (void)nx, (void)ny, (void)h;
+    const int r = rr - 2;
+    const int gx = x0 + 4 * c, gy = y0 + r;
+    if (gx >= ld)
+        return;
+    const long long q = (long long)gy * ld + gx;
+    T *vs = svy + rr * TX + 4 * c;
+    const Chunk<T> vin = ldg_chunk(vs);
+    const Chunk<T> m1 = ldg_chunk(sm1y + rr * TX + 4 * c);
+    const T *ps = sp + r * SW + 4 * c;
+    const Chunk<T> pa = ldg_chunk(ps - SW), pb = ldg_chunk(ps), pc = ldg_chunk(ps + SW), pd = ldg_chunk(ps + 2 * SW);
+    const bool owned = r >= 0 && r < TY && gy < ny;
+    Chunk<T> out = vin, g1 = {}, ia = {}, ib = {}, ic = {}, id = {};
+    if (ADJ && owned) {
+        g1 = ldg_chunk(P.g1y + q);
+        const T *pis = spi + r * SW + 4 * c;
+        ia = ldg_chunk(pis - SW), ib = ldg_chunk(pis), ic = ldg_chunk(pis + SW), id = ldg_chunk(pis + 2 * SW);
+    }
+    T ca = (T)0, cb = (T)0, cs[4];
+    int cq[4];
+    {
+        const int J = gy + 1;
+        const bool rowin = SPC && J >= 1 && J <= ny - 1 && (J <= h || J >= ny - h);
+        const int jj = J <= h ? J : J - ny + 2 * h + 1;
+        if (rowin) {
+            ca = P.a_yh[jj - 1];
+            cb = P.b_yh[jj - 1];
+        }
+    #pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int I = gx + e + 1;
+            const bool in = rowin && I <= nx;
+            cq[e] = in ? (jj - 1) * nx + (I - 1) : -1;
+            cs[e] = in ? P.psi_y_in[cq[e]] : (T)0;
+        }
+    }
+    #pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int I = gx + e + 1, J = gy + 1;
+        if (SPC && !(I <= nx && J >= 1 && J <= ny - 1))
+            continue;
+        CT D = fd4<T, CT>(P, pa.v[e], pb.v[e], pc.v[e], pd.v[e], P.inv_dy);
+        if (SPC && cq[e] >= 0) {
+            T sn;
+            D = cpml_apply<T, CT>(D, ca, cb, cs[e], sn);
+            if (owned)
+                P.psi_y_out[cq[e]] = sn;
+        }
+        out.v[e] = (T)((CT)vin.v[e] - (CT)m1.v[e] * D);
+        if (ADJ && owned) {
+            const CT Dc = fd4<T, CT>(P, ia.v[e], ib.v[e], ic.v[e], id.v[e], P.inv_dy);
+            g1.v[e] = (T)((CT)g1.v[e] + (CT)out.v[e] * Dc);
+        }
+    }
+    st_chunk(vs, out);
+    if (owned) {
+        st_chunk(P.vy_out + q, out);
+        if (ADJ)
+            st_chunk(P.g1y + q, g1);
+    }
+}
+
+// p_new, injection and m0 correlation of chunk column c of tile row r
+template <class T, class CT, bool ADJ, int TY, bool SPC>
+__device__ __forceinline__ void vd_edge_p(const VdCtx<T> &C, const int r, const int c, const int ie0, const int ie1)
+{
+    const VdFusedParams<T> &P = C.P;
+    T *const sp = C.sp, *const svx = C.svx, *const sm1x = C.sm1x, *const svy = C.svy, *const sm1y = C.sm1y, *const spi = C.spi;
+    const int x0 = C.x0, y0 = C.y0, nx = C.nx, ny = C.ny, h = C.h;
+    const long long ld = C.ld;
+    (void)sp, (void)svx, (void)sm1x, (void)svy, (void)sm1y, (void)spi, (void)nx, (void)ny, (void)h;
+    const int idx = r * NCH + c;
+    const int gx = x0 + 4 * c, gy = y0 + r;
+    if (gx >= ld || gy >= ny)
+        return;
+    const long long q = (long long)gy * ld + gx;
+    Chunk<T> g0 = {}, pm1 = {};
+    if (ADJ) {
+        g0 = ldg_chunk(P.g0 + q);
+        pm1 = ldg_chunk(P.pc_itm1 + q);
+    }
+    const Chunk<T> m0 = ldg_chunk(P.m0 + q);
+    const T *vxs = svx + r * SW + 4 * c;
+    const Chunk<T> xa = ldg_chunk(vxs - 4), xb = ldg_chunk(vxs), xc = ldg_chunk(vxs + 4);
+    const T wx[7] = {xa.v[2], xa.v[3], xb.v[0], xb.v[1], xb.v[2], xb.v[3], xc.v[0]}; // vx at columns 4c-2 .. 4c+4
+    const T *vys = svy + (r + 2) * TX + 4 * c;
+    const Chunk<T> ya = ldg_chunk(vys - 2 * TX), yb = ldg_chunk(vys - TX), yc = ldg_chunk(vys), yd = ldg_chunk(vys + TX);
+    const Chunk<T> pin = ldg_chunk(sp + r * SW + 4 * c);
+    Chunk<T> out = pin;
+    T xa_[4], xb_[4], xs_[4], ya_ = (T)0, yb_ = (T)0, ys_[4];
+    int xq[4], yq[4];
+    {
+        const int J = gy + 1;
+        const bool rowok = SPC && J >= 2 && J <= ny - 1;
+        const bool rowin = rowok && (J <= h + 1 || J >= ny - h);
+        const int jj = J <= h + 1 ? J : J - ny + 2 * h + 2;
+        if (rowin) {
+            ya_ = P.a_y[jj - 1];
+            yb_ = P.b_y[jj - 1];
+        }
+    #pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int I = gx + e + 1;
+            const bool ok = rowok && I >= 2 && I <= nx - 1;
+            const bool inx = ok && (I <= h + 1 || I >= nx - h);
+            const int ii = I <= h + 1 ? I : I - nx + 2 * h + 2;
+            xq[e] = inx ? (J - 1) * (2 * (h + 1)) + (ii - 1) : -1;
+            xa_[e] = inx ? P.a_x[ii - 1] : (T)0;
+            xb_[e] = inx ? P.b_x[ii - 1] : (T)0;
+            xs_[e] = inx ? P.xi_x_in[xq[e]] : (T)0;
+            const bool iny = ok && rowin;
+            yq[e] = iny ? (jj - 1) * nx + (I - 1) : -1;
+            ys_[e] = iny ? P.xi_y_in[yq[e]] : (T)0;
+        }
+    }
+    #pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int I = gx + e + 1, J = gy + 1;
+        if (SPC && !(I >= 2 && I <= nx - 1 && J >= 2 && J <= ny - 1))
+            continue; // update_p_CPML! touches interior cells only
+        // d vx / dx at I-1 (backward staggered): vx[I-2 .. I+1]
+        CT Dx = fd4<T, CT>(P, wx[e], wx[e + 1], wx[e + 2], wx[e + 3], P.inv_dx);
+        if (SPC && xq[e] >= 0) {
+            T sn;
+            Dx = cpml_apply<T, CT>(Dx, xa_[e], xb_[e], xs_[e], sn);
+            P.xi_x_out[xq[e]] = sn;
+        }
+        CT Dy = fd4<T, CT>(P, ya.v[e], yb.v[e], yc.v[e], yd.v[e], P.inv_dy);
+        if (SPC && yq[e] >= 0) {
+            T sn;
+            Dy = cpml_apply<T, CT>(Dy, ya_, yb_, ys_[e], sn);
+            P.xi_y_out[yq[e]] = sn;
+        }
+        out.v[e] = (T)((CT)pin.v[e] - (CT)m0.v[e] * (Dx + Dy));
+    }
+    // inject_sources!: entries of this tile in source-index order (deterministic for coincident sources)
+    for (int e = ie0; e < ie1; ++e) {
+        const int cell = P.inj_cell[e];
+        if ((cell >> 2) == idx)
+            out.v[cell & 3] = out.v[cell & 3] + P.inj_tf[(size_t)P.inj_idx[e] * P.inj_nt + (P.inj_it - 1)];
+    }
+    if (ADJ) { // grad_m0 = grad_m0 - adjp * (p_it - p_itm1) * (1/dt), all in T (correlate_gradient_xPU.jl:12-21)
+        const Chunk<T> pit = ldg_chunk(spi + r * SW + 4 * c);
+    #pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const T d = pit.v[e] - pm1.v[e];
+            const T t = out.v[e] * d;
+            g0.v[e] = g0.v[e] - t * P.inv_dt;
+        }
+        st_chunk(P.g0 + q, g0);
+    }
+    st_chunk(P.p_out + q, out);
+}
+
 // Tile rows are issued bottom strip rows first, then from the top: the rows that touch the bottom C-PML strip run the slow
 // generic body and would otherwise form a tail of long CTAs at the end of the grid.
 template <int TY>
@@ -188,128 +429,59 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
     }
 
     if (P.do_v) {
+        const VdCtx<T> C{P, sp, svx, sm1x, svy, sm1y, spi, x0, y0, nx, ny, h, ld};
         // ---- phase 2a: vx_new on columns -4 .. TX+3 (chunks -1 .. NCH), rows 0 .. TY-1 --------------------
-        for (int idx = tid; idx < TY * (NCH + 2); idx += NTHR) {
-            const int r = idx / (NCH + 2), c = idx - r * (NCH + 2) - 1;
-            const int gx = x0 + 4 * c, gy = y0 + r; // 0-based global column of the chunk's first cell / row
-            if (gx >= ld)
-                continue;
-            const long long q = (long long)gy * ld + gx;
-            T *vs = svx + r * SW + 4 * c;
-            const Chunk<T> vin = ldg_chunk(vs);
-            const Chunk<T> m1 = ldg_chunk(sm1x + r * SW + 4 * c);
-            const T *ps = sp + r * SW + 4 * c; // p at column 4c
-            const Chunk<T> pa = ldg_chunk(ps - 4), pb = ldg_chunk(ps), pc = ldg_chunk(ps + 4);
-            const T w[7] = {pa.v[3], pb.v[0], pb.v[1], pb.v[2], pb.v[3], pc.v[0], pc.v[1]};
-            const bool owned = c >= 0 && c < NCH && gy < ny;
-            Chunk<T> out = vin, g1 = {};
-            T wi[7];
-            if (ADJ && owned) {
-                g1 = ldg_chunk(P.g1x + q);
-                const T *pis = spi + r * SW + 4 * c;
-                const Chunk<T> ia = ldg_chunk(pis - 4), ib = ldg_chunk(pis), ic = ldg_chunk(pis + 4);
-                wi[0] = ia.v[3], wi[1] = ib.v[0], wi[2] = ib.v[1], wi[3] = ib.v[2], wi[4] = ib.v[3], wi[5] = ic.v[0], wi[6] = ic.v[1];
+        {
+            // plain chunk columns [ca, cb): all four cells inside 1 .. nx-1 and outside the x strips; rows below the grid do nothing
+            const int nr = min(TY, ny - y0);
+            int ca = NCH + 1, cb = NCH + 1;
+            for (int c = NCH; c >= -1; --c) {
+                const int gx = x0 + 4 * c;
+                const bool plain = gx >= max(h, 0) && gx + 4 <= nx - h - 1;
+                if (plain)
+                    ca = c;
+                else if (ca == NCH + 1)
+                    cb = c;
             }
-            // C-PML values of the chunk's cells are fetched together before use (one dependent global load per cell otherwise)
-            T ca[4], cb[4], cs[4];
-            int cq[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int I = gx + e + 1, J = gy + 1;
-                const bool in = edge && (I >= 1 && I <= nx - 1 && J <= ny) && (I <= h || I >= nx - h);
-                const int ii = I <= h ? I : I - nx + 2 * h + 1;
-                cq[e] = in ? (J - 1) * (2 * h) + (ii - 1) : -1;
-                ca[e] = in ? P.a_xh[ii - 1] : (T)0;
-                cb[e] = in ? P.b_xh[ii - 1] : (T)0;
-                cs[e] = in ? P.psi_x_in[cq[e]] : (T)0;
+            if (ca == NCH + 1)
+                ca = cb = -1; // no plain column
+            for (int idx = tid; idx < nr * (NCH + 2); idx += NTHR) {
+                const int r = idx / (NCH + 2), c = idx - r * (NCH + 2) - 1;
+                if (c >= ca && c < cb)
+                    vd_edge_vx<T, CT, ADJ, TY, false>(C, r, c);
             }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int I = gx + e + 1, J = gy + 1; // 1-based reference indices
-                if (edge && !(I >= 1 && I <= nx - 1 && J <= ny))
-                    continue; // outside update_vx_CPML!'s range: stays as it is (zero)
-                CT D = fd4<T, CT>(P, w[e], w[e + 1], w[e + 2], w[e + 3], P.inv_dx);
-                if (edge && cq[e] >= 0) {
-                    T sn;
-                    D = cpml_apply<T, CT>(D, ca[e], cb[e], cs[e], sn);
-                    if (owned)
-                        P.psi_x_out[cq[e]] = sn;
-                }
-                out.v[e] = (T)((CT)vin.v[e] - (CT)m1.v[e] * D);
-                if (ADJ && owned) {
-                    const CT Dc = fd4<T, CT>(P, wi[e], wi[e + 1], wi[e + 2], wi[e + 3], P.inv_dx);
-                    g1.v[e] = (T)((CT)g1.v[e] + (CT)out.v[e] * Dc);
-                }
-            }
-            st_chunk(vs, out);
-            if (owned) {
-                st_chunk(P.vx_out + q, out);
-                if (ADJ)
-                    st_chunk(P.g1x + q, g1);
+            const int ncs = (ca + 1) + (NCH + 1 - cb);
+            for (int idx = tid; idx < nr * ncs; idx += NTHR) {
+                const int r = idx / ncs, j = idx - r * ncs;
+                vd_edge_vx<T, CT, ADJ, TY, true>(C, r, j < ca + 1 ? j - 1 : cb + (j - (ca + 1)));
             }
         }
 
         // ---- phase 2b: vy_new on rows -2 .. TY, columns 0 .. TX-1 -----------------------------------------
-        for (int idx = tid; idx < (TY + 3) * NCH; idx += NTHR) {
-            const int rr = idx / NCH, c = idx - rr * NCH;
-            const int r = rr - 2;
-            const int gx = x0 + 4 * c, gy = y0 + r;
-            if (gx >= ld)
-                continue;
-            const long long q = (long long)gy * ld + gx;
-            T *vs = svy + rr * TX + 4 * c;
-            const Chunk<T> vin = ldg_chunk(vs);
-            const Chunk<T> m1 = ldg_chunk(sm1y + rr * TX + 4 * c);
-            const T *ps = sp + r * SW + 4 * c;
-            const Chunk<T> pa = ldg_chunk(ps - SW), pb = ldg_chunk(ps), pc = ldg_chunk(ps + SW), pd = ldg_chunk(ps + 2 * SW);
-            const bool owned = r >= 0 && r < TY && gy < ny;
-            Chunk<T> out = vin, g1 = {}, ia = {}, ib = {}, ic = {}, id = {};
-            if (ADJ && owned) {
-                g1 = ldg_chunk(P.g1y + q);
-                const T *pis = spi + r * SW + 4 * c;
-                ia = ldg_chunk(pis - SW), ib = ldg_chunk(pis), ic = ldg_chunk(pis + SW), id = ldg_chunk(pis + 2 * SW);
+        {
+            // plain rows [ra, rb) of the staged rows 0 .. TY+2 (tile row rr - 2): 1-based J = y0 + rr - 1 inside (h, ny - h); plain
+            // columns [0, cb): all four cells <= nx
+            const int ra = min(max(h + 2 - y0, 0), TY + 3), rb = min(max(ny - h - y0 + 1, ra), TY + 3);
+            const int cb = min(max((nx - x0) / 4, 0), NCH);
+            for (int idx = tid; idx < (TY + 3) * NCH; idx += NTHR) {
+                const int rr = idx / NCH, c = idx - rr * NCH;
+                if (rr >= ra && rr < rb && c < cb)
+                    vd_edge_vy<T, CT, ADJ, TY, false>(C, rr, c);
             }
-            T ca = (T)0, cb = (T)0, cs[4];
-            int cq[4];
-            {
-                const int J = gy + 1;
-                const bool rowin = edge && J >= 1 && J <= ny - 1 && (J <= h || J >= ny - h);
-                const int jj = J <= h ? J : J - ny + 2 * h + 1;
-                if (rowin) {
-                    ca = P.a_yh[jj - 1];
-                    cb = P.b_yh[jj - 1];
+            const int nrs = ra + (TY + 3 - rb), ncs = NCH - cb;
+            const int n1 = nrs * NCH, n2 = (rb - ra) * ncs;
+            for (int idx = tid; idx < n1 + n2; idx += NTHR) {
+                int rr, c;
+                if (idx < n1) {
+                    const int i = idx / NCH;
+                    c = idx - i * NCH;
+                    rr = i < ra ? i : rb + (i - ra);
+                } else {
+                    const int t2 = idx - n1, i = t2 / ncs;
+                    rr = ra + i;
+                    c = cb + (t2 - i * ncs);
                 }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int I = gx + e + 1;
-                    const bool in = rowin && I <= nx;
-                    cq[e] = in ? (jj - 1) * nx + (I - 1) : -1;
-                    cs[e] = in ? P.psi_y_in[cq[e]] : (T)0;
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int I = gx + e + 1, J = gy + 1;
-                if (edge && !(I <= nx && J >= 1 && J <= ny - 1))
-                    continue;
-                CT D = fd4<T, CT>(P, pa.v[e], pb.v[e], pc.v[e], pd.v[e], P.inv_dy);
-                if (edge && cq[e] >= 0) {
-                    T sn;
-                    D = cpml_apply<T, CT>(D, ca, cb, cs[e], sn);
-                    if (owned)
-                        P.psi_y_out[cq[e]] = sn;
-                }
-                out.v[e] = (T)((CT)vin.v[e] - (CT)m1.v[e] * D);
-                if (ADJ && owned) {
-                    const CT Dc = fd4<T, CT>(P, ia.v[e], ib.v[e], ic.v[e], id.v[e], P.inv_dy);
-                    g1.v[e] = (T)((CT)g1.v[e] + (CT)out.v[e] * Dc);
-                }
-            }
-            st_chunk(vs, out);
-            if (owned) {
-                st_chunk(P.vy_out + q, out);
-                if (ADJ)
-                    st_chunk(P.g1y + q, g1);
+                vd_edge_vy<T, CT, ADJ, TY, true>(C, rr, c);
             }
         }
         if (!P.do_p)
@@ -319,88 +491,42 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
 
     // ---- phase 3: p_new on the tile, injection, m0 correlation -------------------------------------------
     const int ie0 = P.inj_it > 0 ? P.inj_off[tile] : 0, ie1 = P.inj_it > 0 ? P.inj_off[tile + 1] : 0;
-    for (int idx = tid; idx < TY * NCH; idx += NTHR) {
-        const int r = idx / NCH, c = idx - r * NCH;
-        const int gx = x0 + 4 * c, gy = y0 + r;
-        if (gx >= ld || gy >= ny)
-            continue;
-        const long long q = (long long)gy * ld + gx;
-        Chunk<T> g0 = {}, pm1 = {};
-        if (ADJ) {
-            g0 = ldg_chunk(P.g0 + q);
-            pm1 = ldg_chunk(P.pc_itm1 + q);
+    {
+        const VdCtx<T> C{P, sp, svx, sm1x, svy, sm1y, spi, x0, y0, nx, ny, h, ld};
+        // plain rows [ra, rb): 1-based J = y0 + r + 1 in [max(2, h+2), ny-h-1]; plain chunk columns [ca, cb): I likewise
+        const int lo = max(2, h + 2);
+        const int ra = min(max(lo - y0 - 1, 0), TY), rb = min(max(ny - h - 1 - y0, ra), TY);
+        int ca = NCH, cb = NCH;
+        for (int c = NCH - 1; c >= 0; --c) {
+            const int gx = x0 + 4 * c;
+            const bool plain = gx + 1 >= lo && gx + 4 <= nx - h - 1;
+            if (plain)
+                ca = c;
+            else if (ca == NCH)
+                cb = c;
         }
-        const Chunk<T> m0 = ldg_chunk(P.m0 + q);
-        const T *vxs = svx + r * SW + 4 * c;
-        const Chunk<T> xa = ldg_chunk(vxs - 4), xb = ldg_chunk(vxs), xc = ldg_chunk(vxs + 4);
-        const T wx[7] = {xa.v[2], xa.v[3], xb.v[0], xb.v[1], xb.v[2], xb.v[3], xc.v[0]}; // vx at columns 4c-2 .. 4c+4
-        const T *vys = svy + (r + 2) * TX + 4 * c;
-        const Chunk<T> ya = ldg_chunk(vys - 2 * TX), yb = ldg_chunk(vys - TX), yc = ldg_chunk(vys), yd = ldg_chunk(vys + TX);
-        const Chunk<T> pin = ldg_chunk(sp + r * SW + 4 * c);
-        Chunk<T> out = pin;
-        T xa_[4], xb_[4], xs_[4], ya_ = (T)0, yb_ = (T)0, ys_[4];
-        int xq[4], yq[4];
-        {
-            const int J = gy + 1;
-            const bool rowok = edge && J >= 2 && J <= ny - 1;
-            const bool rowin = rowok && (J <= h + 1 || J >= ny - h);
-            const int jj = J <= h + 1 ? J : J - ny + 2 * h + 2;
-            if (rowin) {
-                ya_ = P.a_y[jj - 1];
-                yb_ = P.b_y[jj - 1];
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int I = gx + e + 1;
-                const bool ok = rowok && I >= 2 && I <= nx - 1;
-                const bool inx = ok && (I <= h + 1 || I >= nx - h);
-                const int ii = I <= h + 1 ? I : I - nx + 2 * h + 2;
-                xq[e] = inx ? (J - 1) * (2 * (h + 1)) + (ii - 1) : -1;
-                xa_[e] = inx ? P.a_x[ii - 1] : (T)0;
-                xb_[e] = inx ? P.b_x[ii - 1] : (T)0;
-                xs_[e] = inx ? P.xi_x_in[xq[e]] : (T)0;
-                const bool iny = ok && rowin;
-                yq[e] = iny ? (jj - 1) * nx + (I - 1) : -1;
-                ys_[e] = iny ? P.xi_y_in[yq[e]] : (T)0;
-            }
+        if (ca == NCH)
+            ca = cb = 0; // no plain column
+        for (int idx = tid; idx < TY * NCH; idx += NTHR) {
+            const int r = idx / NCH, c = idx - r * NCH;
+            if (r >= ra && r < rb && c >= ca && c < cb)
+                vd_edge_p<T, CT, ADJ, TY, false>(C, r, c, ie0, ie1);
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int I = gx + e + 1, J = gy + 1;
-            if (edge && !(I >= 2 && I <= nx - 1 && J >= 2 && J <= ny - 1))
-                continue; // update_p_CPML! touches interior cells only
-            // d vx / dx at I-1 (backward staggered): vx[I-2 .. I+1]
-            CT Dx = fd4<T, CT>(P, wx[e], wx[e + 1], wx[e + 2], wx[e + 3], P.inv_dx);
-            if (edge && xq[e] >= 0) {
-                T sn;
-                Dx = cpml_apply<T, CT>(Dx, xa_[e], xb_[e], xs_[e], sn);
-                P.xi_x_out[xq[e]] = sn;
+        const int nrs = ra + (TY - rb), ncs = ca + (NCH - cb);
+        const int n1 = nrs * NCH, n2 = (rb - ra) * ncs;
+        for (int idx = tid; idx < n1 + n2; idx += NTHR) {
+            int r, c;
+            if (idx < n1) {
+                const int i = idx / NCH;
+                c = idx - i * NCH;
+                r = i < ra ? i : rb + (i - ra);
+            } else {
+                const int t2 = idx - n1, i = t2 / ncs, j = t2 - i * ncs;
+                r = ra + i;
+                c = j < ca ? j : cb + (j - ca);
             }
-            CT Dy = fd4<T, CT>(P, ya.v[e], yb.v[e], yc.v[e], yd.v[e], P.inv_dy);
-            if (edge && yq[e] >= 0) {
-                T sn;
-                Dy = cpml_apply<T, CT>(Dy, ya_, yb_, ys_[e], sn);
-                P.xi_y_out[yq[e]] = sn;
-            }
-            out.v[e] = (T)((CT)pin.v[e] - (CT)m0.v[e] * (Dx + Dy));
+            vd_edge_p<T, CT, ADJ, TY, true>(C, r, c, ie0, ie1);
         }
-        // inject_sources!: entries of this tile in source-index order (deterministic for coincident sources)
-        for (int e = ie0; e < ie1; ++e) {
-            const int cell = P.inj_cell[e];
-            if ((cell >> 2) == idx)
-                out.v[cell & 3] = out.v[cell & 3] + P.inj_tf[(size_t)P.inj_idx[e] * P.inj_nt + (P.inj_it - 1)];
-        }
-        if (ADJ) { // grad_m0 = grad_m0 - adjp * (p_it - p_itm1) * (1/dt), all in T (correlate_gradient_xPU.jl:12-21)
-            const Chunk<T> pit = ldg_chunk(spi + r * SW + 4 * c);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const T d = pit.v[e] - pm1.v[e];
-                const T t = out.v[e] * d;
-                g0.v[e] = g0.v[e] - t * P.inv_dt;
-            }
-            st_chunk(P.g0 + q, g0);
-        }
-        st_chunk(P.p_out + q, out);
     }
 }
 
