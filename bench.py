@@ -369,8 +369,8 @@ def run_b200(args):
             dur = kt_ms / kt_n * 1e-3
             ach = bytes_per_cell * n * n / dur / 1e9
             roof = {"bound": "hbm", "kernel": dominant_kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": 585.0e6 if (args.grid == 4096 and args.fast_f32) else None,
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one forward launch, ncu --set full (profiles/r1_ncu_vd_fwd3_fast.txt)",
+                    "traffic": 583.2e6 if (args.grid == 4096 and args.fast_f32) else None,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one forward launch, ncu --set full (profiles/r1_ncu_vd_fwd_v6.txt)",
                     "peak_source": peak_src, "frac_of_8TBs_nominal": ach / 8000.0, "avg_launch_us": dur * 1e6, "timed_launches": kt_n,
                     "algorithmic_bytes_per_launch": bytes_per_cell * n * n,
                     "sampling": "CUDA events on the engine's stream around each forward-sweep graph (nt step launches + the checkpoint "
