@@ -33,6 +33,7 @@
 #include "ela_fused.h"
 #include "tma.cuh"
 #include "kernels.h"
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -560,16 +561,15 @@ __device__ __forceinline__ void disp_task(const TileCtx<T, TZ, ADJ> &C, const in
 // Tile rows are issued bottom strip rows first, then from the top: the rows that touch the bottom C-PML strip run the slow
 // per-cell body and would otherwise form a tail of long CTAs at the end of the grid.
 template <int TZ>
-__device__ __forceinline__ int tile_row(int halo)
+__device__ __forceinline__ int tile_row(int halo, int nty, int brow)
 {
-    const int nty = (int)gridDim.y;
     const int nedge = min(nty, (halo + TZ + 3 + TZ - 1) / TZ);
-    const int by = (int)blockIdx.y + nty - nedge;
+    const int by = brow + nty - nedge;
     return by >= nty ? by - nty : by;
 }
 
 template <class T, class CT, int TZ, bool ADJ, bool EDGE>
-__device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, TZ, ADJ> &S)
+__device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, TZ, ADJ> &S, const int bx, const int trow)
 {
     constexpr int V = 16 / (int)sizeof(T);
     constexpr int NV = W / V;   // vectors per staged row
@@ -578,13 +578,12 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
     constexpr int NP3 = TZ * NVT / NTHR; // vectors per thread in the displacement update
     static_assert(TZ * NVT % NTHR == 0, "tile rows must split evenly over the CTA");
     const int tid = threadIdx.x;
-    const int trow = tile_row<TZ>(P.halo);
-    const int x0 = blockIdx.x * TX, z0 = trow * TZ;
+    const int x0 = bx * TX, z0 = trow * TZ;
     const int nx = P.nx, nz = P.nz, h = P.halo;
     const long long ld = P.ld;
     const bool ft = P.freetop != 0;
     const int j0 = ft ? 1 : 2;
-    const int tile = trow * gridDim.x + blockIdx.x;
+    const int tile = trow * P.ntx + bx;
     const T idx_ = P.inv_dx, idz_ = P.inv_dz;
     // does the tile's stress region reach an x / a z strip (or edge)?  ∂̃ is the identity elsewhere (CTA-uniform tests)
     const int mm = max(h + 1, 2);
@@ -748,20 +747,44 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
 }
 #undef MAD
 
-template <class T, class CT, int TZ, bool ADJ>
-__global__ void __launch_bounds__(NTHR, 2) ela_fused_kernel(const __grid_constant__ ElaFusedParams<T> P)
+// PART 0: every tile in one launch; 1: interior tiles only (edge tiles exit at once); 2: edge tiles only, blockIdx.x enumerates
+// them compactly: the full rows outside [era, erb) first, then the columns outside [eca, ecb) of the rows inside.
+template <class T, class CT, int TZ, bool ADJ, int PART>
+__global__ void __launch_bounds__(NTHR, (PART == 1 && !ADJ && sizeof(T) == 4 && TZ == 16) ? 3 : 2) ela_fused_kernel(const __grid_constant__ ElaFusedParams<T> P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ElaSmem<T, TZ, ADJ> &S = *reinterpret_cast<ElaSmem<T, TZ, ADJ> *>(smem_raw);
-    const int x0 = blockIdx.x * TX, z0 = tile_row<TZ>(P.halo) * TZ;
+    int bx, trow;
+    if (PART == 2) {
+        const int t = (int)blockIdx.x;
+        const int nrs = P.era + (P.ntz - P.erb), n1 = nrs * P.ntx;
+        if (t < n1) {
+            const int i = t / P.ntx;
+            bx = t - i * P.ntx;
+            trow = i < (P.ntz - P.erb) ? P.erb + i : i - (P.ntz - P.erb); // bottom strip rows first
+        } else {
+            const int ncs = P.eca + (P.ntx - P.ecb), t2 = t - n1, i = t2 / ncs, j = t2 - i * ncs;
+            trow = P.era + i;
+            bx = j < P.eca ? j : P.ecb + (j - P.eca);
+        }
+    } else {
+        bx = (int)blockIdx.x;
+        trow = tile_row<TZ>(P.halo, P.ntz, (int)blockIdx.y);
+    }
     // interior tile: every cell of the tile's stress region (1-based indices x0-1 .. x0+TX+2, z0-1 .. z0+TZ+2) lies inside all
-    // update ranges, outside every C-PML strip and below the free-surface rows
-    const int m = max(P.halo + 1, 2);
-    const bool interior = x0 - 1 > m && x0 + TX + 2 < P.nx - 1 - P.halo && z0 - 1 > (P.top_inactive ? 2 : m) && z0 + TZ + 2 < P.nz - 1 - P.halo;
-    if (interior || P.dbg_all_interior)
-        ela_tile<T, CT, TZ, ADJ, false>(P, S);
-    else
-        ela_tile<T, CT, TZ, ADJ, true>(P, S);
+    // update ranges, outside every C-PML strip and below the free-surface rows (host: ela_interior_range)
+    const bool interior = (trow >= P.era && trow < P.erb && bx >= P.eca && bx < P.ecb) || P.dbg_all_interior;
+    if (PART == 1) {
+        if (interior)
+            ela_tile<T, CT, TZ, ADJ, false>(P, S, bx, trow);
+    } else if (PART == 2) {
+        ela_tile<T, CT, TZ, ADJ, true>(P, S, bx, trow);
+    } else {
+        if (interior)
+            ela_tile<T, CT, TZ, ADJ, false>(P, S, bx, trow);
+        else
+            ela_tile<T, CT, TZ, ADJ, true>(P, S, bx, trow);
+    }
 }
 
 // ---- small kernels on the padded layout ---------------------------------------------------------------------------------
@@ -878,56 +901,84 @@ __global__ void __launch_bounds__(256) elf_dt2_over_rho_kernel(long long ld, lon
 
 } // namespace
 
-template <class T, class CT, int TZ, bool ADJ>
-static void ela_fused_launch_v(const ElaFusedParams<T> &P0, cudaStream_t st)
+template <class T, class CT, int TZ, bool ADJ, int PART>
+static void ela_fused_launch_p(const ElaFusedParams<T> &P, dim3 grd, cudaStream_t st)
 {
-    static const int dbg = [] { const char *e = std::getenv("SWB_ELF_DEBUG_ALL_INTERIOR"); return e ? std::atoi(e) : 0; }();
-    ElaFusedParams<T> P = P0;
-    P.dbg_all_interior = dbg;
-    const dim3 grd(cdiv(P.nx, TX), cdiv(P.nz, TZ), 1);
     const size_t smem = sizeof(ElaSmem<T, TZ, ADJ>);
     int dev = 0;
     SWB_CUDA(cudaGetDevice(&dev));
     static bool done[64] = {}; // opt-in to > 48 KB of dynamic shared memory once per device and instantiation
     if (dev < 64 && !done[dev]) {
-        SWB_CUDA(cudaFuncSetAttribute(ela_fused_kernel<T, CT, TZ, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SWB_CUDA(cudaFuncSetAttribute(ela_fused_kernel<T, CT, TZ, ADJ, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done[dev] = true;
     }
-    ela_fused_kernel<T, CT, TZ, ADJ><<<grd, NTHR, smem, st>>>(P);
+    ela_fused_kernel<T, CT, TZ, ADJ, PART><<<grd, NTHR, smem, st>>>(P);
     check_launch("ela_fused_kernel");
     count_launch();
 }
 
+template <class T, class CT, int TZ, bool ADJ>
+static void ela_fused_launch_v(const ElaFusedParams<T> &P0, cudaStream_t st, cudaStream_t st_edge)
+{
+    static const int dbg = [] { const char *e = std::getenv("SWB_ELF_DEBUG_ALL_INTERIOR"); return e ? std::atoi(e) : 0; }();
+    ElaFusedParams<T> P = P0;
+    P.dbg_all_interior = dbg;
+    P.ntx = (int)cdiv(P.nx, TX);
+    P.ntz = (int)cdiv(P.nz, TZ);
+    // interior tile rows / columns: x0 - 1 > m, x0 + TX + 2 < nx - 1 - halo (likewise z, with m = 2 above an inactive top strip)
+    const int m = std::max(P.halo + 1, 2), mz = P.top_inactive ? 2 : m;
+    auto range = [](int n_tiles, int t, int lo_excl, int hi_excl, int &a, int &b) { // tiles i with i*t - 1 > lo_excl and i*t + t + 2 < hi_excl
+        a = n_tiles, b = n_tiles;
+        for (int i = n_tiles - 1; i >= 0; --i) {
+            const bool in = i * t - 1 > lo_excl && i * t + t + 2 < hi_excl;
+            if (in)
+                a = i;
+            else if (a == n_tiles)
+                b = i;
+        }
+        if (a == n_tiles)
+            a = b = 0;
+    };
+    range(P.ntx, TX, m, P.nx - 1 - P.halo, P.eca, P.ecb);
+    range(P.ntz, TZ, mz, P.nz - 1 - P.halo, P.era, P.erb);
+    const int n_int = (P.erb - P.era) * (P.ecb - P.eca), n_edge = P.ntx * P.ntz - n_int;
+    if (st_edge != nullptr && n_int > 0 && n_edge > 0 && !dbg) {
+        ela_fused_launch_p<T, CT, TZ, ADJ, 1>(P, dim3(P.ntx, P.ntz, 1), st);
+        ela_fused_launch_p<T, CT, TZ, ADJ, 2>(P, dim3(n_edge, 1, 1), st_edge);
+    } else
+        ela_fused_launch_p<T, CT, TZ, ADJ, 0>(P, dim3(P.ntx, P.ntz, 1), st);
+}
+
 template <class T, class CT, int TZ>
-static void ela_fused_launch_a(const ElaFusedParams<T> &P, cudaStream_t st)
+static void ela_fused_launch_a(const ElaFusedParams<T> &P, cudaStream_t st, cudaStream_t st_edge)
 {
     if (P.corr)
-        ela_fused_launch_v<T, CT, TZ, true>(P, st);
+        ela_fused_launch_v<T, CT, TZ, true>(P, st, st_edge);
     else
-        ela_fused_launch_v<T, CT, TZ, false>(P, st);
+        ela_fused_launch_v<T, CT, TZ, false>(P, st, st_edge);
 }
 
 template <>
-void ela_fused_launch<float>(const ElaFusedParams<float> &P, bool fast, cudaStream_t st)
+void ela_fused_launch<float>(const ElaFusedParams<float> &P, bool fast, cudaStream_t st, cudaStream_t st_edge)
 {
     SWB_REQUIRE(P.tz == 16 || P.tz == 24, "fused elastic step: unsupported tile height");
     if (fast) {
         if (P.tz == 16)
-            ela_fused_launch_a<float, float, 16>(P, st);
+            ela_fused_launch_a<float, float, 16>(P, st, st_edge);
         else
-            ela_fused_launch_a<float, float, 24>(P, st);
+            ela_fused_launch_a<float, float, 24>(P, st, st_edge);
     } else {
         if (P.tz == 16)
-            ela_fused_launch_a<float, double, 16>(P, st);
+            ela_fused_launch_a<float, double, 16>(P, st, st_edge);
         else
-            ela_fused_launch_a<float, double, 24>(P, st);
+            ela_fused_launch_a<float, double, 24>(P, st, st_edge);
     }
 }
 template <>
-void ela_fused_launch<double>(const ElaFusedParams<double> &P, bool, cudaStream_t st)
+void ela_fused_launch<double>(const ElaFusedParams<double> &P, bool, cudaStream_t st, cudaStream_t st_edge)
 {
     SWB_REQUIRE(P.tz == 8, "fused elastic step: unsupported tile height");
-    ela_fused_launch_a<double, double, 8>(P, st);
+    ela_fused_launch_a<double, double, 8>(P, st, st_edge);
 }
 
 void elf_dt2_over_rho(int dtype, long long ld, long long w, long long hgt, const void *rho, void *fac, double dt, cudaStream_t st)

@@ -25,6 +25,8 @@ struct ElaFusedParams {
     // TMA descriptors of the padded planes staged through shared memory: ux, uz (current), λ, μ, μ_ihalf_jhalf, forward ux, uz [it-1]
     alignas(64) CUtensorMap tm[7];
     int nx, nz, halo, freetop, tz;
+    int ntx, ntz;           // tile grid
+    int era, erb, eca, ecb; // interior tiles (plain expressions everywhere): tile rows [era, erb) x tile columns [eca, ecb)
     int top_inactive; // the top C-PML strip has a = 0 (free surface): its memory variables stay 0 and ∂̃ = ∂ there
     long long ld;
     T inv_dx, inv_dz, dt;
@@ -62,12 +64,15 @@ struct ElaFusedParams {
     int dbg_all_interior; // timing experiment only (SWB_ELF_DEBUG_ALL_INTERIOR=1): wrong results in the strips
 };
 
+// st_edge != nullptr: the interior tiles and the edge tiles (C-PML strips, grid edges, free surface) run as two kernels, the edge
+// one on st_edge beside the interior one (disjoint tiles, both read only the previous time levels; the caller forks / joins the
+// streams): the interior kernel then carries none of the per-cell code and fits one more CTA per SM.
 template <class T>
-void ela_fused_launch(const ElaFusedParams<T> &P, bool fast, cudaStream_t st);
+void ela_fused_launch(const ElaFusedParams<T> &P, bool fast, cudaStream_t st, cudaStream_t st_edge);
 template <>
-void ela_fused_launch<float>(const ElaFusedParams<float> &P, bool fast, cudaStream_t st);
+void ela_fused_launch<float>(const ElaFusedParams<float> &P, bool fast, cudaStream_t st, cudaStream_t st_edge);
 template <>
-void ela_fused_launch<double>(const ElaFusedParams<double> &P, bool fast, cudaStream_t st);
+void ela_fused_launch<double>(const ElaFusedParams<double> &P, bool fast, cudaStream_t st, cudaStream_t st_edge);
 
 // tensor map of a whole padded plane (plane_base = first guard row), box = ELF_SW columns x box_rows rows
 void elf_make_tmap(CUtensorMap *out, int dtype, const void *plane_base, long long ld, long long rows, int box_rows);
