@@ -306,36 +306,45 @@ __device__ __forceinline__ void stress_task(const TileCtx<T, TZ, ADJ> &C, const 
 #pragma unroll
     for (int k = 0; k < V; ++k)
         dudx_c[k] = dudx[k], dwdz_c[k] = dwdz[k], dwdx_c[k] = dwdx[k], dudz_c[k] = dudz[k];
-    if (SP) { // ∂̃: ψ_∂ux∂x (4), ψ_∂uz∂z (7) for σxx, σzz; ψ_∂uz∂x (5), ψ_∂ux∂z (6) for σxz
+    if (SP) { // ∂̃ by direction (a tile usually reaches the strips of one direction only): x: ψ_∂ux∂x (4) for σxx, σzz and ψ_∂uz∂x (5)
+              // for σxz; z: ψ_∂uz∂z (7) and ψ_∂ux∂z (6).  Both kinds of a direction are fetched before either is used.
         int ka[V], kb[V], oa[V], ob[V];
         bool st[V];
         CpmlVec<T, V> ca, cb;
-        const int kz7 = zs ? cpml_k(J - 1, nz - 1, h, 1) : 0, kz6 = zs ? cpml_k(J, nz, h, 0) : 0;
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            const int c = c0 + k, I = x0 + c + 1;
+            const int c = c0 + k;
             st[k] = r >= 0 && r < TZ && c >= 0 && c < TX;
-            ka[k] = (xs && v1[k]) ? cpml_k(I - 1, nx - 1, h, 1) : 0;
-            oa[k] = (J - 1) * (2 * (h + 1)) + (ka[k] - 1);
-            kb[k] = v1[k] ? kz7 : 0;
-            ob[k] = (I - 1) + (kz7 - 1) * nx;
         }
-        cpml_fetch<T, V>(ca, ka, oa, P.a_x, P.b_x, P.psi_in[4]);
-        cpml_fetch<T, V>(cb, kb, ob, P.a_z, P.b_z, P.psi_in[7]);
-        cpml_finish<T, CT, V>(dudx_c, ca, ka, oa, st, P.psi_out[4]);
-        cpml_finish<T, CT, V>(dwdz_c, cb, kb, ob, st, P.psi_out[7]);
+        if (xs) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-            const int I = x0 + c0 + k + 1;
-            ka[k] = (xs && v2[k]) ? cpml_k(I, nx, h, 0) : 0;
-            oa[k] = (J - 1) * (2 * h) + (ka[k] - 1);
-            kb[k] = v2[k] ? kz6 : 0;
-            ob[k] = (I - 1) + (kz6 - 1) * (nx - 1);
+            for (int k = 0; k < V; ++k) {
+                const int I = x0 + c0 + k + 1;
+                ka[k] = v1[k] ? cpml_k(I - 1, nx - 1, h, 1) : 0;
+                oa[k] = (J - 1) * (2 * (h + 1)) + (ka[k] - 1);
+                kb[k] = v2[k] ? cpml_k(I, nx, h, 0) : 0;
+                ob[k] = (J - 1) * (2 * h) + (kb[k] - 1);
+            }
+            cpml_fetch<T, V>(ca, ka, oa, P.a_x, P.b_x, P.psi_in[4]);
+            cpml_fetch<T, V>(cb, kb, ob, P.a_xh, P.b_xh, P.psi_in[5]);
+            cpml_finish<T, CT, V>(dudx_c, ca, ka, oa, st, P.psi_out[4]);
+            cpml_finish<T, CT, V>(dwdx_c, cb, kb, ob, st, P.psi_out[5]);
         }
-        cpml_fetch<T, V>(ca, ka, oa, P.a_xh, P.b_xh, P.psi_in[5]);
-        cpml_fetch<T, V>(cb, kb, ob, P.a_zh, P.b_zh, P.psi_in[6]);
-        cpml_finish<T, CT, V>(dwdx_c, ca, ka, oa, st, P.psi_out[5]);
-        cpml_finish<T, CT, V>(dudz_c, cb, kb, ob, st, P.psi_out[6]);
+        const int kz7 = zs ? cpml_k(J - 1, nz - 1, h, 1) : 0, kz6 = zs ? cpml_k(J, nz, h, 0) : 0;
+        if (kz7 > 0 || kz6 > 0) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int I = x0 + c0 + k + 1;
+                ka[k] = v1[k] ? kz7 : 0;
+                oa[k] = (I - 1) + (kz7 - 1) * nx;
+                kb[k] = v2[k] ? kz6 : 0;
+                ob[k] = (I - 1) + (kz6 - 1) * (nx - 1);
+            }
+            cpml_fetch<T, V>(ca, ka, oa, P.a_z, P.b_z, P.psi_in[7]);
+            cpml_fetch<T, V>(cb, kb, ob, P.a_zh, P.b_zh, P.psi_in[6]);
+            cpml_finish<T, CT, V>(dwdz_c, ca, ka, oa, st, P.psi_out[7]);
+            cpml_finish<T, CT, V>(dudz_c, cb, kb, ob, st, P.psi_out[6]);
+        }
     }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
@@ -479,34 +488,38 @@ __device__ __forceinline__ void disp_task(const TileCtx<T, TZ, ADJ> &C, const in
         else
             b2[k] = inner4<T, CT>(zm1[k], z0v[k], zp1[k], zp2[k], idz_);
     }
-    if (SP) { // ∂̃: ψ_∂σxx∂x (0), ψ_∂σxz∂z (3) for ux; ψ_∂σxz∂x (1), ψ_∂σzz∂z (2) for uz
+    if (SP) { // ∂̃ by direction: x: ψ_∂σxx∂x (0) for ux, ψ_∂σxz∂x (1) for uz; z: ψ_∂σxz∂z (3) for ux, ψ_∂σzz∂z (2) for uz
         int ka[V], kb[V], oa[V], ob[V];
         CpmlVec<T, V> ca, cb;
+        if (xs) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int I = x0 + c0 + k + 1;
+                ka[k] = vx[k] ? cpml_k(I, nx, h, 0) : 0;
+                oa[k] = (J - 1) * (2 * h) + (ka[k] - 1);
+                kb[k] = vz[k] ? cpml_k(I - 1, nx - 1, h, 1) : 0;
+                ob[k] = (J - 1) * (2 * (h + 1)) + (kb[k] - 1);
+            }
+            cpml_fetch<T, V>(ca, ka, oa, P.a_xh, P.b_xh, P.psi_in[0]);
+            cpml_fetch<T, V>(cb, kb, ob, P.a_x, P.b_x, P.psi_in[1]);
+            cpml_finish<T, CT, V>(a1, ca, ka, oa, vx, P.psi_out[0]);
+            cpml_finish<T, CT, V>(b1, cb, kb, ob, vz, P.psi_out[1]);
+        }
         const int kz3 = zs ? cpml_k(J - 1, nz - 1, h, 1) : 0, kz2 = zs ? cpml_k(J, nz, h, 0) : 0;
+        if (kz3 > 0 || kz2 > 0) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-            const int I = x0 + c0 + k + 1;
-            ka[k] = (xs && vx[k]) ? cpml_k(I, nx, h, 0) : 0;
-            oa[k] = (J - 1) * (2 * h) + (ka[k] - 1);
-            kb[k] = vx[k] ? kz3 : 0;
-            ob[k] = (I - 1) + (kz3 - 1) * (nx - 1);
+            for (int k = 0; k < V; ++k) {
+                const int I = x0 + c0 + k + 1;
+                ka[k] = vx[k] ? kz3 : 0;
+                oa[k] = (I - 1) + (kz3 - 1) * (nx - 1);
+                kb[k] = vz[k] ? kz2 : 0;
+                ob[k] = (I - 1) + (kz2 - 1) * nx;
+            }
+            cpml_fetch<T, V>(ca, ka, oa, P.a_z, P.b_z, P.psi_in[3]);
+            cpml_fetch<T, V>(cb, kb, ob, P.a_zh, P.b_zh, P.psi_in[2]);
+            cpml_finish<T, CT, V>(a2, ca, ka, oa, vx, P.psi_out[3]);
+            cpml_finish<T, CT, V>(b2, cb, kb, ob, vz, P.psi_out[2]);
         }
-        cpml_fetch<T, V>(ca, ka, oa, P.a_xh, P.b_xh, P.psi_in[0]);
-        cpml_fetch<T, V>(cb, kb, ob, P.a_z, P.b_z, P.psi_in[3]);
-        cpml_finish<T, CT, V>(a1, ca, ka, oa, vx, P.psi_out[0]);
-        cpml_finish<T, CT, V>(a2, cb, kb, ob, vx, P.psi_out[3]);
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-            const int I = x0 + c0 + k + 1;
-            ka[k] = (xs && vz[k]) ? cpml_k(I - 1, nx - 1, h, 1) : 0;
-            oa[k] = (J - 1) * (2 * (h + 1)) + (ka[k] - 1);
-            kb[k] = vz[k] ? kz2 : 0;
-            ob[k] = (I - 1) + (kz2 - 1) * nx;
-        }
-        cpml_fetch<T, V>(ca, ka, oa, P.a_x, P.b_x, P.psi_in[1]);
-        cpml_fetch<T, V>(cb, kb, ob, P.a_zh, P.b_zh, P.psi_in[2]);
-        cpml_finish<T, CT, V>(b1, ca, ka, oa, vz, P.psi_out[1]);
-        cpml_finish<T, CT, V>(b2, cb, kb, ob, vz, P.psi_out[2]);
     }
 #pragma unroll
     for (int k = 0; k < V; ++k) {

@@ -125,3 +125,16 @@ def test_slab_partition_and_routing():
         idx = np.stack([np.zeros(nz, dtype=np.int64), np.zeros(nz, dtype=np.int64), np.arange(nz)], axis=1)
         routed = np.concatenate([slab_route_points(idx, nz, world, r) for r in range(world)])
         assert sorted(routed.tolist()) == list(range(nz))  # every point has exactly one owner
+
+
+def test_julia_extension_binds_only_exported_symbols():
+    """ext/SeismicWaves_B200BackendExt.jl is the reference-side binding of the C ABI: every symbol it
+    ccalls must be declared in include/swb200.h and exported by libswb200.so, so the boundary cannot drift unnoticed."""
+    import swb200 as S
+
+    lib = S._lib.load()
+    src = open(os.path.join(ROOT, "ext", "SeismicWaves_B200BackendExt.jl")).read()
+    bound = sorted(set(re.findall(r":(swb_[a-z0-9_]+)", src)))
+    assert len(bound) >= 20, bound
+    missing = [s for s in bound if s not in S._lib.EXPORTS or not hasattr(lib, s)]
+    assert not missing, missing

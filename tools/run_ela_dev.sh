@@ -10,5 +10,3 @@ for cfg in "f32 1" "f32 0" "f64 0"; do
   $B --dtype $1 --fast-f32 $2 2>&1 | tail -1 | tee -a gpurun_out/ela_timings.log
 done
 SWB_ELF_TZ=16 $B --dtype f32 --fast-f32 1 2>&1 | tail -1 | tee -a gpurun_out/ela_timings.log
-SWB_ELF_TZ=24 $B --dtype f32 --fast-f32 1 2>&1 | tail -1 | tee -a gpurun_out/ela_timings.log
-SWB_ELF_SINGLE_KERNEL=1 $B --dtype f32 --fast-f32 1 2>&1 | tail -1 | tee -a gpurun_out/ela_timings.log
