@@ -200,6 +200,8 @@ def workload_config(_, args, note=None):
          "l2_policy": "working set per sweep (>= 600 MB) exceeds the 126 MB L2, no flush needed"}
     if args.grid != 4096 or args.nt != 1000:
         c["workload"] = f"REDUCED (not the headline config): 2D acoustic VD {args.grid}x{args.grid} Float32 nt={args.nt}"
+    elif args.check_freq and args.check_freq != 31:
+        c["workload"] = c["workload"].replace("check_freq=31", f"check_freq={args.check_freq} (NOT the headline check_freq=31)")
     if note:
         c["note"] = note
     return c
