@@ -41,8 +41,16 @@ namespace swb {
 
 int elf_tz(int dtype, bool adjoint)
 {
-    if (dtype == SWB_F64)
-        return 8;
+    if (dtype == SWB_F64) {
+        static const int tz64 = [] {
+            const char *e = std::getenv("SWB_ELF_TZ64");
+            const int v = e ? std::atoi(e) : 0;
+            return (v == 8 || v == 12) ? v : 0;
+        }();
+        if (tz64)
+            return tz64;
+        return adjoint ? 8 : 12; // 12 rows: two forward CTAs still fit (96 KB each); the correlating adjoint launch needs 8
+    }
     // measured at 4096 x 2048 (profiles/): forward 24 rows 83 us vs 16 rows 86 us; adjoint + correlation 16 rows 183 us vs 24 rows 196 us
     static const int tz_env = [] {
         const char *e = std::getenv("SWB_ELF_TZ");
@@ -990,8 +998,11 @@ void ela_fused_launch<float>(const ElaFusedParams<float> &P, bool fast, cudaStre
 template <>
 void ela_fused_launch<double>(const ElaFusedParams<double> &P, bool, cudaStream_t st, cudaStream_t st_edge)
 {
-    SWB_REQUIRE(P.tz == 8, "fused elastic step: unsupported tile height");
-    ela_fused_launch_a<double, double, 8>(P, st, st_edge);
+    SWB_REQUIRE(P.tz == 8 || P.tz == 12, "fused elastic step: unsupported tile height");
+    if (P.tz == 8)
+        ela_fused_launch_a<double, double, 8>(P, st, st_edge);
+    else
+        ela_fused_launch_a<double, double, 12>(P, st, st_edge);
 }
 
 void elf_dt2_over_rho(int dtype, long long ld, long long w, long long hgt, const void *rho, void *fac, double dt, cudaStream_t st)
