@@ -72,7 +72,8 @@ class WaveSimulation:
         d.freetop = int(cpmlparams.freeboundtop)
         d.gradient = int(self.gradient)
         d.check_freq = gradparams.check_freq if (gradparams is not None and self.gradient) else 1
-        d.flags = (_lib.SWB_FLAG_FAST_F32 if runparams.fast_f32 else 0) | (0 if runparams.fused else _lib.SWB_FLAG_NO_FUSION)
+        d.flags = ((_lib.SWB_FLAG_FAST_F32 if runparams.fast_f32 else 0) | (0 if runparams.fused else _lib.SWB_FLAG_NO_FUSION)
+                   | (0 if getattr(runparams, "graphs", True) else _lib.SWB_FLAG_NO_GRAPH))
         self._h = C.c_void_p()
         _lib.check(self.lib.swb_sim_create(C.byref(d), C.byref(self._h)))
         self.matprop = None

@@ -81,6 +81,7 @@ class RunParameters:
     device: int = 0
     fast_f32: bool = False   # pure-Float32 arithmetic instead of the reference's Float64 intermediates
     fused: bool = True       # fused engine kernels (False: one launch per reference kernel)
+    graphs: bool = True      # replay the per-shot time loops as CUDA graphs (False: eager launches, SWB_FLAG_NO_GRAPH)
 
     def __post_init__(self):
         assert self.minPPW >= 0

@@ -125,7 +125,7 @@ def oracle_gradient(case, observed, check_freq=1, mute_src=0, mute_rec=0, comput
 
 
 def product_inputs(case, observed=None, fast_f32=False, fused=True, check_freq=1, mute_src=0, mute_rec=0, compute_misfit=True, interp_method="arithmetic",
-                   snapevery=None):
+                   snapevery=None, graphs=True):
     import swb200 as S
 
     T = case["dtype"].type
@@ -141,7 +141,7 @@ def product_inputs(case, observed=None, fast_f32=False, fused=True, check_freq=1
         srcs = S.ScalarSources(s["src_positions"].astype(T), s["src_tf"].astype(T), T(s["domfreq"]))
         recs = S.ScalarReceivers(s["rec_positions"].astype(T), case["nt"], dtype=case["dtype"])
         shots.append(S.ScalarShot(srcs=srcs, recs=recs))
-    runparams = S.RunParameters(parall="B200", fast_f32=fast_f32, fused=fused, snapevery=snapevery, erroronPPW=False)
+    runparams = S.RunParameters(parall="B200", fast_f32=fast_f32, fused=fused, graphs=graphs, snapevery=snapevery, erroronPPW=False)
     gradparams = S.GradParameters(mute_radius_src=mute_src, mute_radius_rec=mute_rec, compute_misfit=compute_misfit, check_freq=check_freq)
     misfit = None
     if observed is not None:

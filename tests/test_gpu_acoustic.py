@@ -327,3 +327,23 @@ def test_cd_fused_points_on_faces_and_fast_f32():
     (gref, _), _, _ = oracle_gradient(case, observed, check_freq=7)
     (ggot, _), _ = _gradient_product(case, observed, check_freq=7, fused=True, fast_f32=True)
     assert rel_l2(ggot["vp"], gref["vp"]) <= tol(np.float32)
+
+
+@pytest.mark.parametrize("kind,n", [("acoustic_vd", (300, 170)), ("acoustic_cd", (300, 170)), ("acoustic_cd", (70, 45, 80))])
+def test_eager_launches_equal_graph_replay(kind, n):
+    """SWB_FLAG_NO_GRAPH: the same launch sequence enqueued eagerly (two shots: the second one replays the captured graphs)"""
+    case = acoustic_case(kind=kind, n=n, nt=80, halo=10, dtype=np.float32, seed=9, nshots=2, nrec=12)
+    for sh in case["shots"]:  # shallow sources: the wave reaches the receivers near the top within nt steps
+        sh["src_positions"][:, -1] = 14.0 * case["h"]
+    res = {}
+    for graphs in (True, False):
+        seis, _ = _forward_product(case, graphs=graphs)
+        observed = make_observed(case, seis)
+        res[graphs] = (seis, _gradient_product(case, observed, check_freq=9, graphs=graphs)[0])
+    for a, b in zip(res[True][0], res[False][0]):
+        assert np.max(np.abs(a)) > 0
+        assert np.array_equal(a, b)
+    (ga, ma), (gb, mb) = res[True][1], res[False][1]
+    for k in ga:
+        assert np.array_equal(ga[k], gb[k]), k
+    assert ma == mb

@@ -10,7 +10,7 @@ from elastic_cases import elastic_case, make_observed, oracle_forward, oracle_gr
 pytestmark = pytest.mark.gpu
 
 
-def product_inputs(case, observed=None, check_freq=1, mute_src=0, mute_rec=0, fast_f32=False, snapevery=None, fused=True):
+def product_inputs(case, observed=None, check_freq=1, mute_src=0, mute_rec=0, fast_f32=False, snapevery=None, fused=True, graphs=True):
     import swb200 as S
 
     T = case["dtype"].type
@@ -27,7 +27,7 @@ def product_inputs(case, observed=None, check_freq=1, mute_src=0, mute_rec=0, fa
         else:
             srcs = S.ExternalForceSources(s["src_positions"].astype(T), s["src_tf"].astype(T), T(s["domfreq"]))
             shots.append(S.ExternalForceShot(srcs=srcs, recs=recs))
-    runparams = S.RunParameters(parall="B200", fast_f32=fast_f32, fused=fused, snapevery=snapevery, erroronPPW=False)
+    runparams = S.RunParameters(parall="B200", fast_f32=fast_f32, fused=fused, graphs=graphs, snapevery=snapevery, erroronPPW=False)
     gradparams = S.GradParameters(mute_radius_src=mute_src, mute_radius_rec=mute_rec, compute_misfit=True, check_freq=check_freq)
     misfit = [S.L2Misfit(observed=o) for o in observed] if observed is not None else None
     return params, matprop, shots, misfit, runparams, gradparams
@@ -207,5 +207,30 @@ def test_fused_equals_unfused_bitwise_production_halo(dtype, n, freetop, halo):
     (ga, ma), (gb, mb) = grads[True], grads[False]
     for k in ga:
         assert np.max(np.abs(ga[k])) > 0
+        assert np.array_equal(ga[k], gb[k]), k
+    assert ma == mb
+
+
+@pytest.mark.parametrize("kind", ["momten", "extforce"])
+def test_eager_launches_equal_graph_replay(kind):
+    """SWB_FLAG_NO_GRAPH: the same launch sequence (side-stream receiver sums, fused correlation) enqueued eagerly"""
+    import swb200 as S
+
+    case = elastic_case(n=(300, 140), nt=60, halo=8, dtype=np.float32, kind=kind, nshots=2, nsrc=2, nrec=5, seed=33)
+    for s in case["shots"]:
+        s["src_positions"][:, 1] = np.array([15.2, 21.7])[: s["src_positions"].shape[0]] * case["h"]
+    res = {}
+    for graphs in (True, False):
+        params, matprop, shots, _, runparams, _ = product_inputs(case, graphs=graphs)
+        S.swforward(params, matprop, shots, runparams=runparams)
+        seis = [sh.recs.seismograms.copy() for sh in shots]
+        obs = make_observed(case, seis)
+        params, matprop, shots, misfit, runparams, gradparams = product_inputs(case, observed=obs, check_freq=7, graphs=graphs)
+        res[graphs] = (seis, S.swgradient(params, matprop, shots, misfit, runparams=runparams, gradparams=gradparams))
+    for a, b in zip(res[True][0], res[False][0]):
+        assert np.max(np.abs(a)) > 0
+        assert np.array_equal(a, b)
+    (ga, ma), (gb, mb) = res[True][1], res[False][1]
+    for k in ga:
         assert np.array_equal(ga[k], gb[k]), k
     assert ma == mb
