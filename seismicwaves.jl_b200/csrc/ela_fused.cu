@@ -195,7 +195,7 @@ struct ElaSmem {
     T ux[UH * W], uz[UH * W];                     // displacements, rows -4 .. TZ+3, columns -4 .. TX+3 (TMA destinations: 128-byte aligned)
     T sxx[SH * W], szz[SH * W], sxz[SH * W];      // λ, μ, μ_ihalf_jhalf, then the stresses: rows -2 .. TZ+1
     T fx[ADJ ? SH * W : 8], fz[ADJ ? SH * W : 8]; // forward u[it-1] for the correlation, rows -2 .. TZ+1
-    unsigned long long bar;
+    unsigned long long bar, bar2; // mbarriers of the two row halves of the staged working set
     static_assert(TZ % 4 == 0, "rows x 544 bytes must be a multiple of 128");
 };
 
@@ -261,6 +261,12 @@ __device__ __forceinline__ void stress_task(const TileCtx<T, TZ, ADJ> &C, const 
     const int ou = (rr + 2) * W + vv * V;  // ... in ux / uz
     const int os = rr * W + vv * V;        // ... in the stress / factor / forward-field arrays
     const int J = z0 + r + 1;              // 1-based reference row
+    {   // rows whose inputs (ux, uz rows rr .. rr+4, factors row rr, forward fields rows rr-2 .. rr+2) reach into the second half
+        constexpr int UH1 = elf_half_rows(TZ + 8, sizeof(T)), SH1 = elf_half_rows(TZ + 4, sizeof(T));
+        constexpr int RR1 = (UH1 - 4) < (ADJ ? SH1 - 2 : SH1) ? (UH1 - 4) : (ADJ ? SH1 - 2 : SH1);
+        if (rr >= RR1)
+            mbar_wait(&S.bar2, 0);
+    }
     if (SP && (J < 1 || J > nz - 1)) {     // outside every update range: zero stresses
         T zero_[V];
 #pragma unroll
@@ -612,18 +618,33 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
     const bool zs = EDGE && !((P.top_inactive || z0 - 1 > mm) && z0 + TZ + 2 < nz - 1 - h);
 
     // ---- phase 1: one thread requests the shared-memory working set (TMA), all threads their owned uold and dt²/ρ ----------
+    //      The working set arrives in two row halves on two mbarriers: the stress rows that need only the first half start while the
+    //      second half is still in flight.
     if (tid == 0) {
+        constexpr int UH1 = elf_half_rows(UH, sizeof(T)), SH1 = elf_half_rows(SH, sizeof(T));
+        static_assert(UH - UH1 == UH1, "the halves of ux / uz share one descriptor");
         mbar_init(&S.bar, 1);
-        constexpr unsigned bytes = (unsigned)((2 * UH + (ADJ ? 5 : 3) * SH) * W * sizeof(T));
-        mbar_expect_tx(&S.bar, bytes);
-        tma_load_2d(S.ux, &P.tm[0], x0 - 4, ELF_GB + z0 - 4, &S.bar);
-        tma_load_2d(S.uz, &P.tm[1], x0 - 4, ELF_GB + z0 - 4, &S.bar);
-        tma_load_2d(S.sxx, &P.tm[2], x0 - 4, ELF_GB + z0 - 2, &S.bar);
-        tma_load_2d(S.szz, &P.tm[3], x0 - 4, ELF_GB + z0 - 2, &S.bar);
-        tma_load_2d(S.sxz, &P.tm[4], x0 - 4, ELF_GB + z0 - 2, &S.bar);
+        mbar_init(&S.bar2, 1);
+        mbar_expect_tx(&S.bar, (unsigned)((2 * UH1 + (ADJ ? 5 : 3) * SH1) * W * sizeof(T)));
+        mbar_expect_tx(&S.bar2, (unsigned)((2 * (UH - UH1) + (ADJ ? 5 : 3) * (SH - SH1)) * W * sizeof(T)));
+        const int yu = ELF_GB + z0 - 4, ys = ELF_GB + z0 - 2;
+        tma_load_2d(S.ux, &P.tm[0], x0 - 4, yu, &S.bar);
+        tma_load_2d(S.uz, &P.tm[1], x0 - 4, yu, &S.bar);
+        tma_load_2d(S.sxx, &P.tm[2], x0 - 4, ys, &S.bar);
+        tma_load_2d(S.szz, &P.tm[3], x0 - 4, ys, &S.bar);
+        tma_load_2d(S.sxz, &P.tm[4], x0 - 4, ys, &S.bar);
         if (ADJ) {
-            tma_load_2d(S.fx, &P.tm[5], x0 - 4, ELF_GB + z0 - 2, &S.bar);
-            tma_load_2d(S.fz, &P.tm[6], x0 - 4, ELF_GB + z0 - 2, &S.bar);
+            tma_load_2d(S.fx, &P.tm[5], x0 - 4, ys, &S.bar);
+            tma_load_2d(S.fz, &P.tm[6], x0 - 4, ys, &S.bar);
+        }
+        tma_load_2d(S.ux + UH1 * W, &P.tm[0], x0 - 4, yu + UH1, &S.bar2);
+        tma_load_2d(S.uz + UH1 * W, &P.tm[1], x0 - 4, yu + UH1, &S.bar2);
+        tma_load_2d(S.sxx + SH1 * W, &P.tm[7], x0 - 4, ys + SH1, &S.bar2);
+        tma_load_2d(S.szz + SH1 * W, &P.tm[8], x0 - 4, ys + SH1, &S.bar2);
+        tma_load_2d(S.sxz + SH1 * W, &P.tm[9], x0 - 4, ys + SH1, &S.bar2);
+        if (ADJ) {
+            tma_load_2d(S.fx + SH1 * W, &P.tm[10], x0 - 4, ys + SH1, &S.bar2);
+            tma_load_2d(S.fz + SH1 * W, &P.tm[11], x0 - 4, ys + SH1, &S.bar2);
         }
     }
     T r_uxo[NP3][V], r_uzo[NP3][V], r_fi[NP3][V], r_fj[NP3][V];
@@ -685,6 +706,7 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
             stress_task<T, CT, TZ, ADJ, true>(C, rr, vv);
         }
     }
+    mbar_wait(&S.bar2, 0); // (every thread observes the second half itself before phase 3 reads ux, uz)
     __syncthreads();
     inject_mt<T, TZ, ADJ>(P, S, tile, tid);
 

@@ -23,7 +23,9 @@ inline size_t elf_origin(long long nx) { return (size_t)elf_ld(nx) * ELF_GB; }
 template <class T>
 struct ElaFusedParams {
     // TMA descriptors of the padded planes staged through shared memory: ux, uz (current), λ, μ, μ_ihalf_jhalf, forward ux, uz [it-1]
-    alignas(64) CUtensorMap tm[7];
+    // (each array arrives as two row halves on two mbarriers: [0,1] ux, uz; [2..4] factors and [5,6] forward fields, first half;
+    //  [7..9] factors and [10,11] forward fields, second half -- the halves of ux / uz have equal heights and share a descriptor)
+    alignas(64) CUtensorMap tm[12];
     int nx, nz, halo, freetop, tz;
     int ntx, ntz;           // tile grid
     int era, erb, eca, ecb; // interior tiles (plain expressions everywhere): tile rows [era, erb) x tile columns [eca, ecb)
@@ -73,6 +75,13 @@ template <>
 void ela_fused_launch<float>(const ElaFusedParams<float> &P, bool fast, cudaStream_t st, cudaStream_t st_edge);
 template <>
 void ela_fused_launch<double>(const ElaFusedParams<double> &P, bool fast, cudaStream_t st, cudaStream_t st_edge);
+
+// rows of the first of the two halves a staged array of `rows` rows arrives in (a multiple of 4 Float32 / 2 Float64 rows keeps the
+// second half's shared-memory destination 128-byte aligned)
+__host__ __device__ inline constexpr int elf_half_rows(int rows, size_t esize)
+{
+    return esize == 4 ? ((rows / 2 + 3) / 4) * 4 : ((rows / 2 + 1) / 2) * 2;
+}
 
 // tensor map of a whole padded plane (plane_base = first guard row), box = ELF_SW columns x box_rows rows
 void elf_make_tmap(CUtensorMap *out, int dtype, const void *plane_base, long long ld, long long rows, int box_rows);

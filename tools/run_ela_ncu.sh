@@ -1,7 +1,5 @@
 #!/bin/bash
 # ncu --set full of one forward launch and one correlating adjoint launch of the fused elastic kernel at C3 size
 B="python tools/bench_sim.py"
-ncu --set full --clock-control none --import-source on -k regex:ela_fused -s 20 -c 1 -o gpurun_out/ela_fused_v4_fwd $B --kind ela --n 4096 2048 --nt 40 --no-grad --nrec 10 --reps 0 > gpurun_out/ncu_ela_v4.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:ela_fused -s 49 -c 1 -o gpurun_out/ela_fused_v4_adj $B --kind ela --n 4096 2048 --nt 40 --check-freq 10 --nrec 10 --reps 0 >> gpurun_out/ncu_ela_v4.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"ela|elf" -c 200 --csv --log-file gpurun_out/ela_launches_v4.csv $B --kind ela --n 4096 2048 --nt 40 --check-freq 10 --nrec 10 --reps 0 > /dev/null 2>&1
-ls -la gpurun_out/*.ncu-rep
+ncu --set full --clock-control none --import-source on -k regex:ela_fused -s 20 -c 1 -o gpurun_out/ela_fused_v5_fwd $B --kind ela --n 4096 2048 --nt 40 --no-grad --nrec 10 --reps 0 > gpurun_out/ncu_ela_v5.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ela_fused -s 49 -c 1 -o gpurun_out/ela_fused_v5_adj $B --kind ela --n 4096 2048 --nt 40 --check-freq 10 --nrec 10 --reps 0 >> gpurun_out/ncu_ela_v5.log 2>&1
