@@ -304,6 +304,86 @@ function SeismicWaves.swgradient_1shot!(::CPMLBoundaryCondition, model::Union{Ac
     return out
 end
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Elastic P-SV shots through the per-shot engine (ela_forward.jl:4-159, ela_gradient.jl:4-362).  The host part of the reference
+# stays as it is: `possrcrec_scaletf` (ela_models.jl:6-90) spreads the off-grid positions into Kaiser-windowed sinc point lists
+# and scales the source time functions; the lists cross the ABI flattened to CSR (include/swb200.h, swb_sinc_points_host).
+# ---------------------------------------------------------------------------------------------------------------------
+struct SincPointsHost          # mirrors swb_sinc_points_host
+    n::Int64
+    off::Ptr{Int64}
+    ij::Ptr{Int32}
+    coef::Ptr{Cvoid}
+end
+
+# per-position lists (Vector of (npts, 2) index matrices, Vector of coefficient vectors) -> CSR; the points of one position in
+# ascending linear index (the reference iterates a Dict; any fixed order is equivalent up to the summation order of a receiver)
+function csr(ijs::Vector{<:AbstractMatrix{<:Integer}}, vals::Vector{<:AbstractVector{T}}, nx::Int) where {T}
+    off = zeros(Int64, length(ijs) + 1)
+    for k in eachindex(ijs)
+        off[k + 1] = off[k] + size(ijs[k], 1)
+    end
+    ij = zeros(Int32, off[end], 2)
+    co = zeros(T, off[end])
+    for k in eachindex(ijs)
+        order = sortperm([(ijs[k][p, 2] - 1) * nx + ijs[k][p, 1] for p in 1:size(ijs[k], 1)])
+        ij[off[k] + 1:off[k + 1], :] .= ijs[k][order, :]
+        co[off[k] + 1:off[k + 1]] .= vals[k][order]
+    end
+    return off, ij, co
+end
+
+function bind!(model::ElasticIsoCPMLWaveSimulation{T, 2}, shot::Union{MomentTensorShot{T, 2}, ExternalForceShot{T, 2}}) where {T}
+    src_a_ij, src_a_val, src_b_ij, src_b_val, rec_ux_ij, rec_ux_val, rec_uz_ij, rec_uz_val, scal_srctf =
+        SeismicWaves.possrcrec_scaletf(model, shot; sincinterp=model.sincinterp)
+    nx = model.grid.size[1]
+    lists = (csr(src_a_ij, src_a_val, nx), csr(src_b_ij, src_b_val, nx), csr(rec_ux_ij, rec_ux_val, nx), csr(rec_uz_ij, rec_uz_val, nx))
+    GC.@preserve lists scal_srctf begin
+        pts = [SincPointsHost(length(l[1]) - 1, pointer(l[1]), pointer(l[2]), pointer(l[3])) for l in lists]
+        src_pts, rec_pts = pts[1:2], pts[3:4]
+        if shot isa MomentTensorShot          # lists on σxx/σzz and σxz, srctf (nt, nsrc), one moment tensor per source
+            M = shot.srcs.momtens
+            Mxx, Mzz, Mxz = T[m.Mxx for m in M], T[m.Mzz for m in M], T[m.Mxz for m in M]
+            check(ccall((:swb_sim_bind_elastic_shot, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{SincPointsHost}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{SincPointsHost}),
+                engine(model), 1, src_pts, scal_srctf, Mxx, Mzz, Mxz, rec_pts))
+        else                                   # lists on ux and uz, srctf (nt, 2, nsrc)
+            check(ccall((:swb_sim_bind_elastic_shot, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{SincPointsHost}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{SincPointsHost}),
+                engine(model), 2, src_pts, scal_srctf, C_NULL, C_NULL, C_NULL, rec_pts))
+        end
+    end
+end
+
+function SeismicWaves.swforward_1shot!(::CPMLBoundaryCondition, model::ElasticIsoCPMLWaveSimulation{T, 2, <:B200Array},
+                                       shot::Union{MomentTensorShot{T, 2}, ExternalForceShot{T, 2}}) where {T}
+    upload_model!(model)
+    bind!(model, shot)
+    snapevery = model.runparams.snapevery === nothing ? 0 : model.runparams.snapevery
+    check(ccall((:swb_sim_forward, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32), engine(model), shot.recs.seismograms, snapevery))   # (nt, 2, nrec)
+    return nothing
+end
+
+function SeismicWaves.swgradient_1shot!(::CPMLBoundaryCondition, model::ElasticIsoCPMLWaveSimulation{T, 2, <:B200Array},
+                                        shot::Union{MomentTensorShot{T, 2}, ExternalForceShot{T, 2}}, misfit::AbstractMisfit{T}) where {T}
+    h = engine(model)
+    upload_model!(model)
+    bind!(model, shot)
+    check(ccall((:swb_sim_gradient_forward, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), h, shot.recs.seismograms))
+    adjsrc = .-SeismicWaves.∂χ_∂u(misfit, shot.recs)                                   # (nt, 2, nrec), any AbstractMisfit, on the host
+    check(ccall((:swb_sim_gradient_adjoint, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), h, adjsrc))
+    gp = model.gradparams
+    check(ccall((:swb_sim_zero_total_gradient, lib), Int32, (Ptr{Cvoid},), h))
+    # back_interp of the staggered accumulators, mutearoundmultiplepoints!, on the device (ela_gradient.jl:155-190)
+    check(ccall((:swb_sim_accumulate_gradient, lib), Int32, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int32, Int64, Ptr{Cvoid}, Int32), h,
+        size(shot.srcs.positions, 1), shot.srcs.positions, gp.mute_radius_src, size(shot.recs.positions, 1), shot.recs.positions, gp.mute_radius_rec))
+    out = Dict{String, Array{T, 2}}()
+    for (k, name) in enumerate(("rho", "lambda", "mu"))
+        g = zeros(T, model.grid.size...)
+        check(ccall((:swb_sim_get_total_gradient, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}), h, k - 1, g))
+        out[name] = g
+    end
+    return out
+end
+
 # Multi-GPU shot sharding: one task per device, contiguous shot groups from distribsrcs (utils.jl:28-45); the per-device
 # totals are summed with swb_sim_allreduce_total_gradient (NCCL) -- see INTEGRATION.md for the run_swgradient! method.
 
