@@ -123,22 +123,22 @@ __device__ __forceinline__ void record_points(const CdFusedParams<T> &P, const C
 // ---------------------------------------------------------------------------------------------------------------------
 // bulk kernel
 // ---------------------------------------------------------------------------------------------------------------------
+// (bx, by, bz) = block index in the (gdx, gdy, .) bulk grid; lane / ty = thread index in the (32, bdy) block
 template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
-__global__ void __launch_bounds__(HAS_Y ? 32 * CDF_TY : 32 * CDF_W2D, HAS_Y ? (sizeof(CT) == 4 ? (ADJ ? 3 : 4) : 2) : (sizeof(CT) == 4 ? 8 : 4))
-    cd_bulk_kernel(const CdFusedParams<T> P)
+__device__ __forceinline__ void cd_bulk_body(const CdFusedParams<T> &P, const int bx, const int by, const int bz, const int gdx, const int gdy, const int bdy,
+                                             const int lane, const int ty)
 {
     constexpr int V = 16 / (int)sizeof(T);
     constexpr int TX = 32 * V;
     constexpr int TY = HAS_Y ? CDF_TY : 1;
     typedef CVec<T, V> VT;
 
-    const int lane = threadIdx.x, ty = threadIdx.y;
-    const int xt = HAS_Y ? (int)blockIdx.x : (int)(blockIdx.x * blockDim.y) + ty;
+    const int xt = HAS_Y ? bx : bx * bdy + ty;
     const int i0 = xt * TX + lane * V;
-    const int j = HAS_Y ? P.jlo + (int)blockIdx.y * TY + ty : 0;
+    const int j = HAS_Y ? P.jlo + by * TY + ty : 0;
     if (xt * TX >= P.nx || j >= P.jhi)
         return; // warps are independent (no barriers); a warp leaves only as a whole (shuffles below)
-    const int k0 = P.klo + (int)blockIdx.z * P.zc, k1 = min(k0 + P.zc, P.khi);
+    const int k0 = P.klo + bz * P.zc, k1 = min(k0 + P.zc, P.khi);
     const int iv = xt * 32 + lane;
     const bool ld_ok = i0 < P.nx;                   // this lane's vector exists: it feeds the neighbours' shuffles
     const bool st_ok = iv >= P.ivlo && iv < P.ivhi; // this lane's vector belongs to the bulk
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(HAS_Y ? 32 * CDF_TY : 32 * CDF_W2D, HAS_Y ? (s
     const long long ld = P.ld, plane = P.plane;
     long long off = (long long)k0 * plane + (long long)j * ld + i0; // this thread's vector in plane k
     const long long hxo = lane == 0 ? -1 : V;
-    const int cta = ((int)blockIdx.z * (int)gridDim.y + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x;
+    const int cta = (bz * gdy + by) * gdx + bx;
     const bool has_inj = P.inj_it > 0 && P.inj[0].off[cta + 1] > P.inj[0].off[cta];
     const bool has_rec = P.rec_it > 0 && P.rec[0].off[cta + 1] > P.rec[0].off[cta];
 
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(HAS_Y ? 32 * CDF_TY : 32 * CDF_W2D, HAS_Y ? (s
                 lap = lap + d2<CT, FMA>(w2, pm[v], pc[v], pp[v], i2z);
                 out.v[v] = leapfrog<T, CT, FMA>(pc[v], po.v[v], fc.v[v], lap);
             }
-            const int code0 = ((k - k0) * (int)blockDim.y + ty) * TX + lane * V;
+            const int code0 = ((k - k0) * bdy + ty) * TX + lane * V;
             if (has_inj)
                 inject_points<T, V>(P, P.inj[0], cta, code0, out);
             stv<T, V>(P.pnew + off, out);
@@ -245,6 +245,14 @@ __global__ void __launch_bounds__(HAS_Y ? 32 * CDF_TY : 32 * CDF_W2D, HAS_Y ? (s
         hxc = (CT)hx_n;
         off += plane;
     }
+}
+
+template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
+__global__ void __launch_bounds__(HAS_Y ? 32 * CDF_TY : 32 * CDF_W2D, HAS_Y ? (sizeof(CT) == 4 ? (ADJ ? 3 : 4) : 2) : (sizeof(CT) == 4 ? 8 : 4))
+    cd_bulk_kernel(const CdFusedParams<T> P)
+{
+    cd_bulk_body<T, CT, HAS_Y, ADJ, FMA>(P, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)gridDim.x, (int)gridDim.y, (int)blockDim.y, (int)threadIdx.x,
+                                         (int)threadIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -336,12 +344,11 @@ __device__ __forceinline__ void cd_axis_term_vec(CT (&term)[V], const CT (&w1)[2
 }
 
 template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
-__global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? 8 : 4) cd_rim_kernel(const CdFusedParams<T> P)
+__device__ __forceinline__ void cd_rim_body(const CdFusedParams<T> &P, const int cta, const int tid)
 {
     constexpr int V = 16 / (int)sizeof(T);
     typedef CVec<T, V> VT;
-    const int tid = (int)threadIdx.x, cta = (int)blockIdx.x;
-    const long long vid = (long long)blockIdx.x * CDF_RIM_T + tid;
+    const long long vid = (long long)cta * CDF_RIM_T + tid;
     if (vid >= P.nrimvec)
         return;
     int bi = 0;
@@ -444,6 +451,26 @@ __global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? 8 : 4) cd_rim_ker
     }
 }
 
+template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
+__global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? 8 : 4) cd_rim_kernel(const CdFusedParams<T> P)
+{
+    cd_rim_body<T, CT, HAS_Y, ADJ, FMA>(P, (int)blockIdx.x, (int)threadIdx.x);
+}
+
+// Small 2D grids: both CTA kinds in one launch (the 2D bulk CTA and the rim CTA have 128 threads each).  A step of a grid that
+// fills the GPU for a few microseconds is bound by launch and fork / join latency, not by bandwidth: one kernel node per step
+// instead of two parallel ones plus the join.
+static_assert(32 * CDF_W2D == CDF_RIM_T, "the merged 2D launch needs equal CTA sizes");
+template <class T, class CT, bool ADJ, bool FMA>
+__global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? 8 : 4) cd_merged2d_kernel(const CdFusedParams<T> P, const int nbulk, const int gdx)
+{
+    const int b = (int)blockIdx.x;
+    if (b < nbulk)
+        cd_bulk_body<T, CT, false, ADJ, FMA>(P, b % gdx, 0, b / gdx, gdx, 1, CDF_W2D, (int)threadIdx.x & 31, (int)threadIdx.x >> 5);
+    else
+        cd_rim_body<T, CT, false, ADJ, FMA>(P, b - nbulk, (int)threadIdx.x);
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -544,12 +571,32 @@ void cd_fused_fill_geom(CdFusedParams<T> &P, const CdFusedGeom &g)
 }
 
 template <class T>
-void cd_fused_launch(const CdFusedParams<T> &P, const CdFusedGeom &g, bool adj, bool fast, cudaStream_t st, cudaStream_t st_rim)
+void cd_fused_launch(const CdFusedParams<T> &P, const CdFusedGeom &g, bool adj, bool fast, cudaStream_t st, cudaStream_t st_rim, bool merged)
 {
     SWB_REQUIRE(g.gy <= 65535 && g.gz <= 65535, "grid too large for the fused CD launch geometry");
     const dim3 grd(g.gx, g.gy, g.gz), blk(32, g.ty, 1);
     const unsigned nrim = (unsigned)g.ncta_rim();
     const bool f32fast = sizeof(T) == 4 && fast, has_y = g.has_y;
+    if (merged && !has_y && g.gx > 0 && nrim > 0) {
+        const int nbulk = g.gx * g.gz;
+#define SWB_CDF_M(CT, AD, FM)                                                                            \
+    cd_merged2d_kernel<T, CT, AD, FM><<<(unsigned)nbulk + nrim, CDF_RIM_T, 0, st>>>(P, nbulk, g.gx)
+        if (f32fast) {
+            if (adj)
+                SWB_CDF_M(T, true, true);
+            else
+                SWB_CDF_M(T, false, true);
+        } else {
+            if (adj)
+                SWB_CDF_M(double, true, false);
+            else
+                SWB_CDF_M(double, false, false);
+        }
+#undef SWB_CDF_M
+        check_launch("cd_merged2d_kernel");
+        count_launch();
+        return;
+    }
 #define SWB_CDF_GO(CT, HY, AD, FM)                                                      \
     do {                                                                                \
         if (g.gx > 0) {                                                                 \
@@ -587,7 +634,7 @@ void cd_fused_launch(const CdFusedParams<T> &P, const CdFusedGeom &g, bool adj, 
 
 template void cd_fused_fill_geom<float>(CdFusedParams<float> &, const CdFusedGeom &);
 template void cd_fused_fill_geom<double>(CdFusedParams<double> &, const CdFusedGeom &);
-template void cd_fused_launch<float>(const CdFusedParams<float> &, const CdFusedGeom &, bool, bool, cudaStream_t, cudaStream_t);
-template void cd_fused_launch<double>(const CdFusedParams<double> &, const CdFusedGeom &, bool, bool, cudaStream_t, cudaStream_t);
+template void cd_fused_launch<float>(const CdFusedParams<float> &, const CdFusedGeom &, bool, bool, cudaStream_t, cudaStream_t, bool);
+template void cd_fused_launch<double>(const CdFusedParams<double> &, const CdFusedGeom &, bool, bool, cudaStream_t, cudaStream_t, bool);
 
 } // namespace swb

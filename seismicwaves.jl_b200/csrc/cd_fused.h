@@ -89,6 +89,6 @@ void cd_fused_fill_geom(CdFusedParams<T> &P, const CdFusedGeom &g);
 
 // launches the bulk kernel on `st` and the rim kernel on `st_rim` (may equal st)
 template <class T>
-void cd_fused_launch(const CdFusedParams<T> &P, const CdFusedGeom &g, bool adj, bool fast, cudaStream_t st, cudaStream_t st_rim);
+void cd_fused_launch(const CdFusedParams<T> &P, const CdFusedGeom &g, bool adj, bool fast, cudaStream_t st, cudaStream_t st_rim, bool merged = false);
 
 } // namespace swb
