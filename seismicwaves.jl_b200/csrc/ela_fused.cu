@@ -39,27 +39,31 @@
 
 namespace swb {
 
-int elf_tz(int dtype, bool adjoint)
+int elf_tz(int dtype, bool adjoint, long long nx, long long nz)
 {
-    if (dtype == SWB_F64) {
-        static const int tz64 = [] {
-            const char *e = std::getenv("SWB_ELF_TZ64");
-            const int v = e ? std::atoi(e) : 0;
-            return (v == 8 || v == 12) ? v : 0;
-        }();
-        if (tz64)
-            return tz64;
-        return adjoint ? 8 : 12; // 12 rows: two forward CTAs still fit (96 KB each); the correlating adjoint launch needs 8
-    }
-    // measured at 4096 x 2048 (profiles/): forward 24 rows 83 us vs 16 rows 86 us; adjoint + correlation 16 rows 183 us vs 24 rows 196 us
-    static const int tz_env = [] {
+    // candidates, tallest first: the tallest tile that keeps two CTAs per SM is fastest on large grids (measured at 4096 x 2048,
+    // profiles/: Float32 forward 24 rows 75 us vs 16 rows 81 us, adjoint + correlation 16 rows 171 us vs 24 rows 195 us; Float64
+    // forward 12 rows 137 us vs 8 rows 153 us); a small grid takes the tallest height that still yields one CTA per SM, because a
+    // step of a grid that is one partial wave of CTAs is the latency of one tile (load -> stresses -> displacements -> store)
+    static const int env32 = [] {
         const char *e = std::getenv("SWB_ELF_TZ");
         const int v = e ? std::atoi(e) : 0;
-        return (v == 16 || v == 24) ? v : 0;
+        return (v == 8 || v == 16 || v == 24) ? v : 0;
     }();
-    if (tz_env)
-        return tz_env;
-    return adjoint ? 16 : 24;
+    static const int env64 = [] {
+        const char *e = std::getenv("SWB_ELF_TZ64");
+        const int v = e ? std::atoi(e) : 0;
+        return (v == 4 || v == 8 || v == 12) ? v : 0;
+    }();
+    if (dtype == SWB_F64 ? env64 : env32)
+        return dtype == SWB_F64 ? env64 : env32;
+    const int c32f[3] = {24, 16, 8}, c32a[3] = {16, 8, 8}, c64f[3] = {12, 8, 4}, c64a[3] = {8, 4, 4};
+    const int *c = dtype == SWB_F64 ? (adjoint ? c64a : c64f) : (adjoint ? c32a : c32f);
+    const long long ntx = (nx + ELF_TX - 1) / ELF_TX;
+    for (int k = 0; k < 3; ++k)
+        if (k == 2 || ntx * ((nz + c[k] - 1) / c[k]) >= 148)
+            return c[k];
+    return c[2];
 }
 
 // 2D tensor map of a whole padded plane (all guard rows included), box = ELF_SW columns x box_rows rows
@@ -1004,14 +1008,18 @@ static void ela_fused_launch_a(const ElaFusedParams<T> &P, cudaStream_t st, cuda
 template <>
 void ela_fused_launch<float>(const ElaFusedParams<float> &P, bool fast, cudaStream_t st, cudaStream_t st_edge)
 {
-    SWB_REQUIRE(P.tz == 16 || P.tz == 24, "fused elastic step: unsupported tile height");
+    SWB_REQUIRE(P.tz == 8 || P.tz == 16 || P.tz == 24, "fused elastic step: unsupported tile height");
     if (fast) {
-        if (P.tz == 16)
+        if (P.tz == 8)
+            ela_fused_launch_a<float, float, 8>(P, st, st_edge);
+        else if (P.tz == 16)
             ela_fused_launch_a<float, float, 16>(P, st, st_edge);
         else
             ela_fused_launch_a<float, float, 24>(P, st, st_edge);
     } else {
-        if (P.tz == 16)
+        if (P.tz == 8)
+            ela_fused_launch_a<float, double, 8>(P, st, st_edge);
+        else if (P.tz == 16)
             ela_fused_launch_a<float, double, 16>(P, st, st_edge);
         else
             ela_fused_launch_a<float, double, 24>(P, st, st_edge);
@@ -1020,8 +1028,10 @@ void ela_fused_launch<float>(const ElaFusedParams<float> &P, bool fast, cudaStre
 template <>
 void ela_fused_launch<double>(const ElaFusedParams<double> &P, bool, cudaStream_t st, cudaStream_t st_edge)
 {
-    SWB_REQUIRE(P.tz == 8 || P.tz == 12, "fused elastic step: unsupported tile height");
-    if (P.tz == 8)
+    SWB_REQUIRE(P.tz == 4 || P.tz == 8 || P.tz == 12, "fused elastic step: unsupported tile height");
+    if (P.tz == 4)
+        ela_fused_launch_a<double, double, 4>(P, st, st_edge);
+    else if (P.tz == 8)
         ela_fused_launch_a<double, double, 8>(P, st, st_edge);
     else
         ela_fused_launch_a<double, double, 12>(P, st, st_edge);

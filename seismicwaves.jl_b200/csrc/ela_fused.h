@@ -10,7 +10,7 @@ constexpr int ELF_TZ_MAX = 32; // largest tile height any instantiation uses
 constexpr int ELF_GB = 5;      // zero guard rows in front of a padded plane (4 halo rows + the left halo of row -4)
 constexpr int ELF_GA = ELF_TZ_MAX + 8; // zero guard rows behind it
 // tile height in cells, per storage type and launch kind (forward / adjoint): two CTAs fit the 227 KB of shared memory of an SM
-int elf_tz(int dtype, bool adjoint);
+int elf_tz(int dtype, bool adjoint, long long nx, long long nz);
 
 // Padded plane: row pitch ld >= nx + 8 (multiple of 32 elements): at least 4 zero columns after the last cell of a row
 // and 4 before the first cell of the next one, so the 4-point stencils of a tile's halo read zeros outside every
