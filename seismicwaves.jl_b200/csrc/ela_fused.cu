@@ -762,32 +762,28 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
         }
     }
 
-    // ---- external forces / adjoint sources on the owned cells, sources in index order (they may share cells) -----------------
+    // ---- external forces / adjoint sources on the owned cells: one parallel pass per round (see ElaFusedParams::fi_off) --------
     if (P.fi_it > 0) {
-        int e = P.fi_off[tile];
-        const int e1 = P.fi_off[tile + 1];
-        if (e < e1) {
+        const int g0 = P.fi_off[tile], g1 = P.fi_off[tile + 1];
+        if (g0 < g1) {
             __syncthreads(); // the tile's unew is in memory
             const T dt2 = P.dt * P.dt;
-            while (e < e1) {
-                const int s_ = P.fi_src[e];
-                int en = e + 1;
-                while (en < e1 && P.fi_src[en] == s_)
-                    ++en;
-                const T wx = P.fi_tf[((long long)s_ * 2 + 0) * P.nt + (P.fi_it - 1)], wz = P.fi_tf[((long long)s_ * 2 + 1) * P.nt + (P.fi_it - 1)];
-                for (int k = e + tid; k < en; k += NTHR) {
-                    const int cell = P.fi_cell[k];
+            for (int g = g0; g < g1; ++g) {
+                const int e0 = P.fi_roff[g], e1 = P.fi_roff[g + 1];
+                for (int k = e0 + tid; k < e1; k += NTHR) {
+                    const int cell = P.fi_cell[k], s_ = P.fi_src[k];
                     const int comp = cell >= ELF_MT_FIELD ? 1 : 0;
                     const int o = cell - comp * ELF_MT_FIELD;
                     const long long q = (long long)(z0 + o / TX) * ld + (x0 + o % TX);
                     const T cf = P.fi_coef[k];
+                    const T w = P.fi_tf[((long long)s_ * 2 + comp) * P.nt + (P.fi_it - 1)];
                     if (comp == 0)
-                        P.uxn[q] = P.uxn[q] + ((cf * wx) / P.rho_ih[q]) * dt2;
+                        P.uxn[q] = P.uxn[q] + ((cf * w) / P.rho_ih[q]) * dt2;
                     else
-                        P.uzn[q] = P.uzn[q] + ((cf * wz) / P.rho_jh[q]) * dt2;
+                        P.uzn[q] = P.uzn[q] + ((cf * w) / P.rho_jh[q]) * dt2;
                 }
-                __syncthreads();
-                e = en;
+                if (g + 1 < g1)
+                    __syncthreads();
             }
         }
     }

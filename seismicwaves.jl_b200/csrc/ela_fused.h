@@ -51,9 +51,10 @@ struct ElaFusedParams {
     long long nt;
     int mt_it;
     // external-force / adjoint-source injection into the freshly stored unew (inject_external_sources2D! and the residual
-    // injection of adjoint_onestep_CPML!, elastic2D_iso_xPU.jl:96-106,433-440): per-tile lists over the owned cells, grouped
-    // by source in index order; cell = component * ELF_MT_FIELD + row * ELF_TX + column.  fi_it = 0 disables.
-    const int *fi_off, *fi_cell, *fi_src;
+    // injection of adjoint_onestep_CPML!, elastic2D_iso_xPU.jl:96-106,433-440): per-tile lists over the owned cells, split
+    // into rounds (round r = the r-th contribution of every cell, in source order; a round is one parallel pass): fi_off maps a tile
+    // to its rounds, fi_roff a round to its entries; cell = component * ELF_MT_FIELD + row * ELF_TX + column.  fi_it = 0 disables.
+    const int *fi_off, *fi_roff, *fi_cell, *fi_src;
     const T *fi_coef, *fi_tf, *rho_ih, *rho_jh;
     int fi_it;
     // zero-lag correlation fused into an adjoint launch (correlate_gradients!, elastic/backends/shared/

@@ -6,6 +6,7 @@
 // library on the sim's stream; the host sees seismograms, the adjoint source and the finished gradients only.
 #include "engine.h"
 #include "ela_fused.h"
+#include <algorithm>
 #include <cstring>
 
 namespace swb {
