@@ -744,13 +744,9 @@ void launch_one(const VdFusedParams<T> &P, cudaStream_t st)
 
 } // namespace
 
-template <class T>
-void vd_fused_launch(const VdFusedParams<T> &P0, bool fast, cudaStream_t st)
+template <class T, int TY>
+static void vd_fused_launch_ty(const VdFusedParams<T> &P, bool fast, cudaStream_t st)
 {
-    constexpr int TY = VDF_TY;
-    static const int dbg = [] { const char *e = std::getenv("SWB_VD_DEBUG_ALL_INTERIOR"); return e ? std::atoi(e) : 0; }();
-    VdFusedParams<T> P = P0;
-    P.dbg_all_interior = dbg;
     if (sizeof(T) == 8 || !fast) {
         if (P.adj)
             launch_one<T, double, true, TY>(P, st);
@@ -762,6 +758,19 @@ void vd_fused_launch(const VdFusedParams<T> &P0, bool fast, cudaStream_t st)
         else
             launch_one<T, T, false, TY>(P, st);
     }
+}
+
+template <class T>
+void vd_fused_launch(const VdFusedParams<T> &P0, bool fast, cudaStream_t st)
+{
+    static const int dbg = [] { const char *e = std::getenv("SWB_VD_DEBUG_ALL_INTERIOR"); return e ? std::atoi(e) : 0; }();
+    VdFusedParams<T> P = P0;
+    P.dbg_all_interior = dbg;
+    SWB_REQUIRE(P.ty == VDF_TY || P.ty == VDF_TY_SMALL, "fused VD step: unsupported tile height");
+    if (P.ty == VDF_TY)
+        vd_fused_launch_ty<T, VDF_TY>(P, fast, st);
+    else
+        vd_fused_launch_ty<T, VDF_TY_SMALL>(P, fast, st);
 }
 
 template void vd_fused_launch<float>(const VdFusedParams<float> &, bool, cudaStream_t);

@@ -6,7 +6,9 @@
 namespace swb {
 
 constexpr int VDF_TX = 128;          // tile width in cells
-constexpr int VDF_TY = 16;           // tile height in cells
+constexpr int VDF_TY = 16;           // tile height in cells (large grids)
+constexpr int VDF_TY_SMALL = 8;      // ... of grids with fewer than one 16-row tile per SM (a step is the latency of one tile there)
+inline int vdf_ty(long long nx, long long ny) { return ((nx + VDF_TX - 1) / VDF_TX) * ((ny + VDF_TY - 1) / VDF_TY) >= 148 ? VDF_TY : VDF_TY_SMALL; }
 constexpr int PAD_GUARD_BEFORE = 4;  // zero rows in front of a padded plane
 constexpr int PAD_GUARD_AFTER = 36;  // zero rows behind it (>= tile height + 4)
 
@@ -22,7 +24,7 @@ struct VdFusedParams {
     // TMA descriptors of the padded planes staged through shared memory (whole plane incl. guard rows; boxes: p_in VDF_SW x (TY+6),
     // vx_in / m1x VDF_SW x TY, vy_in / m1y VDF_TX x (TY+3), pc_it VDF_SW x (TY+3))
     alignas(64) CUtensorMap tm[6];
-    int nx, ny, halo;
+    int nx, ny, halo, ty; // ty: tile height (VDF_TY or VDF_TY_SMALL)
     long long ld;
     int do_v, do_p, adj;
     T inv_dx, inv_dy, inv_dt;
