@@ -36,7 +36,7 @@ def _csr(idxs, coefs, T):
 class ElasticIsoCPMLWaveSimulation(WaveSimulation):
     kind = _lib.SWB_ELA_ISO
     grad_names = ("rho", "lambda", "mu")
-    _dominant_kernel = "ela_sigma_kernel + ela_u_kernel (two stencil launches per time step)"
+    _dominant_kernel = "ela_fused_kernel (stresses on chip: one stencil launch per time step; adjoint launches carry the five correlations)"
 
     def __init__(self, params, matprop, cpmlparams, runparams, gradparams, gradient: bool = False, sincinterp: bool = True):
         assert len(params.gridsize) == 2, "Only elastic 2D is currently implemented."
