@@ -48,6 +48,8 @@ def test_acoustic_full_size_properties(kind, n, nt):
     _near_surface_geometry(case, src_depth=6.0 if len(n) == 3 else 12.0)
     base = _acoustic_forward(case)[0]
     assert np.max(np.abs(base)) > 0 and np.all(np.isfinite(base))
+    # the fused engine performs the operations of the one-launch-per-reference-kernel path, at full size too
+    assert np.array_equal(_acoustic_forward(case, fused=False)[0], base)
     # linearity: a source 4x as strong gives exactly 4x the seismograms (power of two: every product and sum scales exactly)
     c4 = dict(case, shots=[dict(sh, src_tf=4.0 * sh["src_tf"]) for sh in case["shots"]])
     assert np.array_equal(_acoustic_forward(c4)[0], np.float32(4.0) * base)
