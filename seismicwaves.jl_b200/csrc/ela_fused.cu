@@ -43,7 +43,7 @@ int elf_tz(int dtype, bool adjoint, long long nx, long long nz)
 {
     // candidates, tallest first: the tallest tile that keeps two CTAs per SM is fastest on large grids (measured at 4096 x 2048,
     // profiles/: Float32 forward 24 rows 75 us vs 16 rows 81 us, adjoint + correlation 16 rows 171 us vs 24 rows 195 us; Float64
-    // forward 12 rows 137 us vs 8 rows 153 us); a small grid takes the tallest height that still yields one CTA per SM, because a
+    // forward 12 rows 137 us vs 8 rows 153 us); a small grid takes the tallest height that still yields three CTAs per SM, because a
     // step of a grid that is one partial wave of CTAs is the latency of one tile (load -> stresses -> displacements -> store)
     static const int env32 = [] {
         const char *e = std::getenv("SWB_ELF_TZ");
@@ -61,7 +61,7 @@ int elf_tz(int dtype, bool adjoint, long long nx, long long nz)
     const int *c = dtype == SWB_F64 ? (adjoint ? c64a : c64f) : (adjoint ? c32a : c32f);
     const long long ntx = (nx + ELF_TX - 1) / ELF_TX;
     for (int k = 0; k < 3; ++k)
-        if (k == 2 || ntx * ((nz + c[k] - 1) / c[k]) >= 148)
+        if (k == 2 || ntx * ((nz + c[k] - 1) / c[k]) >= 3 * 148) // measured (Float32 forward): 1024^2 23.1 / 20.3 / 21.4 us at 24 / 16 / 8 rows; 640^2 19.3 / 18.5 / 17.2
             return c[k];
     return c[2];
 }
