@@ -384,9 +384,64 @@ function SeismicWaves.swgradient_1shot!(::CPMLBoundaryCondition, model::ElasticI
     return out
 end
 
-# Multi-GPU shot sharding: one task per device, contiguous shot groups from distribsrcs (utils.jl:28-45); the per-device
-# totals are summed with swb_sim_allreduce_total_gradient (NCCL) -- see INTEGRATION.md for the run_swgradient! method.
-
+# ---------------------------------------------------------------------------------------------------------------------
+# Multi-GPU shot sharding (SURVEY 8e): one simulation per GPU (built with `runparams.device = 0, 1, ...`), one Julia task per
+# simulation, contiguous shot groups from `distribsrcs` (utils.jl:28-45) exactly as the reference's `:threadpersrc` mode
+# (gradient.jl:139-208), per-shot post-processing on the device, then ONE NCCL all-reduce of the per-device totals
+# (`swb_sim_allreduce_total_gradient`) and the result read back from device 0.  Needs JULIA_NUM_THREADS >= number of GPUs: the
+# ranks of one NCCL communicator have to enter `swb_comm_create` and the all-reduce concurrently.
+# The Python twin (`seismicwaves.jl_b200/multigpu.py`, `bench.py --gpus N`) runs the same sequence with one process per GPU.
+# ---------------------------------------------------------------------------------------------------------------------
+function SeismicWaves.run_swgradient!(wavesim::Vector{<:Union{AcousticCDCPMLWaveSimulation{T, N, <:B200Array}, AcousticVDStaggeredCPMLWaveSimulation{T, N, <:B200Array},
+                                                             ElasticIsoCPMLWaveSimulation{T, N, <:B200Array}}},
+                                      matprop::SeismicWaves.MaterialProperties{T, N}, shots::Vector{<:SeismicWaves.Shot{T}},
+                                      misfit::Vector{<:AbstractMisfit{T}}) where {T, N}
+    ndev, nshots = length(wavesim), length(shots)
+    @assert Threads.nthreads() >= ndev "one Julia thread per GPU is needed (NCCL ranks enter collectives concurrently)"
+    for w in wavesim
+        SeismicWaves.check_sim_consistency(w, matprop, shots)
+        SeismicWaves.set_wavesim_matprop!(w, matprop)
+    end
+    id = zeros(UInt8, 128)
+    ndev > 1 && check(ccall((:swb_comm_unique_id, lib), Int32, (Ptr{UInt8},), id))
+    grpshots = SeismicWaves.distribsrcs(nshots, ndev)
+    misfitvals = zeros(T, nshots)
+    compute_misfit = wavesim[1].gradparams.compute_misfit
+    names = wavesim[1] isa AcousticCDCPMLWaveSimulation ? ("vp",) : wavesim[1] isa AcousticVDStaggeredCPMLWaveSimulation ? ("vp", "rho") : ("rho", "lambda", "mu")
+    tasks = map(1:ndev) do r
+        Threads.@spawn begin
+            model, h = wavesim[r], engine(wavesim[r])
+            comm = Ref{Ptr{Cvoid}}(C_NULL)
+            ndev > 1 && check(ccall((:swb_comm_create, lib), Int32, (Ptr{UInt8}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), id, ndev, r - 1, model.runparams.device, comm))
+            upload_model!(model)
+            check(ccall((:swb_sim_zero_total_gradient, lib), Int32, (Ptr{Cvoid},), h))
+            gp = model.gradparams
+            for s in grpshots[r]
+                SeismicWaves.init_shot!(model, shots[s])
+                bind!(model, shots[s])
+                check(ccall((:swb_sim_gradient_forward, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), h, shots[s].recs.seismograms))
+                adjsrc = .-SeismicWaves.∂χ_∂u(misfit[s], shots[s].recs)
+                check(ccall((:swb_sim_gradient_adjoint, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), h, adjsrc))
+                # mute + chain rule of THIS shot, then accumulation into the device-resident total (muting is per shot: it precedes the sum)
+                check(ccall((:swb_sim_accumulate_gradient, lib), Int32, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int32, Int64, Ptr{Cvoid}, Int32), h,
+                    size(shots[s].srcs.positions, 1), shots[s].srcs.positions, gp.mute_radius_src, size(shots[s].recs.positions, 1), shots[s].recs.positions, gp.mute_radius_rec))
+                compute_misfit && (misfitvals[s] = SeismicWaves.calcmisfit(misfit[s], shots[s].recs))
+            end
+            if ndev > 1
+                check(ccall((:swb_sim_allreduce_total_gradient, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), h, comm[]))
+                check(ccall((:swb_comm_destroy, lib), Int32, (Ptr{Cvoid},), comm[]))
+            end
+        end
+    end
+    foreach(wait, tasks)
+    totgrad = Dict{String, Array{T, N}}()
+    for (k, name) in enumerate(names)
+        g = zeros(T, wavesim[1].grid.size...)
+        check(ccall((:swb_sim_get_total_gradient, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}), engine(wavesim[1]), k - 1, g))
+        totgrad[name] = g
+    end
+    return compute_misfit ? (totgrad, sum(misfitvals)) : totgrad
+end
 
 # ---------------------------------------------------------------------------------------------------------------------
 # z-slab decomposition of one 3D acoustic CD forward run (include/swb200.h section 4; no counterpart in the reference).
