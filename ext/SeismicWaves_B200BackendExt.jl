@@ -232,6 +232,13 @@ SeismicWaves.select_backend(::CPMLBoundaryCondition, ::LocalGrid, ::Type{<:Elast
 # Level 2: whole shots on the per-shot engine (performance path)
 # ---------------------------------------------------------------------------------------------------------------------
 const ENGINES = IdDict{Any, Ptr{Cvoid}}()     # wavesim object -> swb_sim*
+# B200-only knobs the reference's RunParameters has no field for: the GPU a simulation lives on (default 0) and the creation flags
+# (SWB_FLAG_FAST_F32 = 1: Float32 arithmetic; SWB_FLAG_NO_FUSION = 2; SWB_FLAG_NO_GRAPH = 4), set before the first shot
+const DEVICE_OF = IdDict{Any, Int32}()
+const FLAGS = Ref{Int32}(0)
+set_device!(model, dev::Integer) = (DEVICE_OF[model] = Int32(dev); model)
+device_of(model) = get(DEVICE_OF, model, Int32(0))
+set_flags!(flags::Integer) = (FLAGS[] = Int32(flags))
 
 simkind(::AcousticCDCPMLWaveSimulation) = Int32(1)
 simkind(::AcousticVDStaggeredCPMLWaveSimulation) = Int32(2)
@@ -242,8 +249,8 @@ function engine(model)
         T = typeof(model.dt)
         N = length(model.grid.size)
         cf = model.gradparams === nothing ? 1 : model.gradparams.check_freq
-        desc = SimDesc(simkind(model), dtype_code(T), N, 0, pad3(Int64.(model.grid.size), Int64(1)), pad3(Float64.(model.grid.spacing), 0.0), Float64(model.dt), model.nt,
-            model.cpmlparams.halo, model.cpmlparams.freeboundtop, model.checkpointer !== nothing, cf, 0, 0)
+        desc = SimDesc(simkind(model), dtype_code(T), N, device_of(model), pad3(Int64.(model.grid.size), Int64(1)), pad3(Float64.(model.grid.spacing), 0.0), Float64(model.dt), model.nt,
+            model.cpmlparams.halo, model.cpmlparams.freeboundtop, model.checkpointer !== nothing, cf, FLAGS[], Int32(0))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:swb_sim_create, lib), Int32, (Ref{SimDesc}, Ref{Ptr{Cvoid}}), desc, h))
         finalizer(_ -> ccall((:swb_sim_destroy, lib), Int32, (Ptr{Cvoid},), h[]), model)
@@ -385,7 +392,7 @@ function SeismicWaves.swgradient_1shot!(::CPMLBoundaryCondition, model::ElasticI
 end
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Multi-GPU shot sharding (SURVEY 8e): one simulation per GPU (built with `runparams.device = 0, 1, ...`), one Julia task per
+# Multi-GPU shot sharding (SURVEY 8e): one simulation per GPU (`set_device!(wavesim[k], k - 1)` before the first shot), one Julia task per
 # simulation, contiguous shot groups from `distribsrcs` (utils.jl:28-45) exactly as the reference's `:threadpersrc` mode
 # (gradient.jl:139-208), per-shot post-processing on the device, then ONE NCCL all-reduce of the per-device totals
 # (`swb_sim_allreduce_total_gradient`) and the result read back from device 0.  Needs JULIA_NUM_THREADS >= number of GPUs: the
@@ -412,7 +419,7 @@ function SeismicWaves.run_swgradient!(wavesim::Vector{<:Union{AcousticCDCPMLWave
         Threads.@spawn begin
             model, h = wavesim[r], engine(wavesim[r])
             comm = Ref{Ptr{Cvoid}}(C_NULL)
-            ndev > 1 && check(ccall((:swb_comm_create, lib), Int32, (Ptr{UInt8}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), id, ndev, r - 1, model.runparams.device, comm))
+            ndev > 1 && check(ccall((:swb_comm_create, lib), Int32, (Ptr{UInt8}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), id, ndev, r - 1, device_of(model), comm))
             upload_model!(model)
             check(ccall((:swb_sim_zero_total_gradient, lib), Int32, (Ptr{Cvoid},), h))
             gp = model.gradparams
