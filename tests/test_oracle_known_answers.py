@@ -180,3 +180,18 @@ def test_distribsrcs():
     assert [list(r) for r in O.distribsrcs(10, 4)] == [[0, 1, 2], [3, 4, 5], [6, 7], [8, 9]]
     assert [list(r) for r in O.distribsrcs(2, 4)] == [[0], [1]]
     assert [list(r) for r in O.distribsrcs(64, 8)] == [list(range(8 * k, 8 * k + 8)) for k in range(8)]
+
+
+def test_snapshotting_criteria_2d():
+    """test/test_snapshotting_constant_density.jl:11-66 re-enacted in 2D (1D kernels are out of scope): one snapshot per
+    `snapevery` steps, none of them empty, consecutive ones different; two shots give two snapshot sets."""
+    from cases import acoustic_case, oracle_forward
+
+    case = acoustic_case(kind="acoustic_cd", n=(72, 66), nt=200, halo=10, freetop=False, dtype=np.float64, seed=12, nshots=2, nsrc=1, nrec=4)
+    _, snaps = oracle_forward(case, snapevery=50)
+    assert snaps is not None and len(snaps) == 2
+    for per_shot in snaps:
+        assert sorted(per_shot.keys()) == [50, 100, 150, 200]
+        fields = [np.asarray(per_shot[it]) for it in sorted(per_shot.keys())]
+        assert all(np.linalg.norm(f) > 0 for f in fields)
+        assert all(not np.allclose(a, b) for a, b in zip(fields[:-1], fields[1:]))
