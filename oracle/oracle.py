@@ -64,6 +64,13 @@ def use_openmp(flag: bool) -> None:
     _USE_OMP = bool(flag)
 
 
+def set_threads(n: int) -> int:
+    """Thread count of the OpenMP build (bench.py's CPU legs); returns the count in effect."""
+    L = lib(True)
+    L.swref_set_num_threads(int(n))
+    return int(L.swref_get_max_threads())
+
+
 def _L() -> C.CDLL:
     return lib(_USE_OMP)
 

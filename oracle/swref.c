@@ -27,6 +27,31 @@
 #undef REAL
 #undef FN
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* thread count of the OpenMP build (the timed CPU baseline).  OMP_NUM_THREADS is read once when libgomp loads, and
+ * torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, so bench.py sets the count explicitly. */
+void swref_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0)
+        omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+int swref_get_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
 int swref_has_openmp(void)
 {
 #ifdef _OPENMP

@@ -136,6 +136,8 @@ class SimBase {
     // a re-bind with the same geometry; returns true if the pointer changed
     bool ensure(DevBuf &b, size_t bytes);
     virtual void pointers_changed() {}
+    // called at the end of set_cpml (cpml_lo_inactive_[axis] is up to date)
+    virtual void cpml_changed(int) {}
     // CUDA-graph replay of a fixed launch sequence: the first call captures `enqueue` on the sim's stream, later calls
     // replay it (SWB_FLAG_NO_GRAPH: always enqueue eagerly).  `updates` = cell-updates the sequence performs.
     struct Graph {

@@ -363,6 +363,7 @@ void SimBase::set_cpml(int axis, const void *a, const void *a_h, const void *b, 
         cpml_lo_inactive_[axis] = lower_half_zero(a, cpml_[axis][0].bytes) && lower_half_zero(a_h, cpml_[axis][1].bytes);
     }
     cpml_set_[axis] = true;
+    cpml_changed(axis);
 }
 
 swb_cpml_axis SimBase::cpml_axis(int ax) const

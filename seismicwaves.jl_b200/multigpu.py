@@ -201,5 +201,8 @@ class SlabForward3D:
         shot.recs.seismograms[...] = full
         return full
 
+    def exchange_mode(self) -> str:
+        return "grouped ncclSend/ncclRecv of one plane per interior face on the engine's stream after every step" if self.sp.world > 1 else "none (single slab)"
+
     def close(self):
         self.sim.close()
