@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SWB_ABI_VERSION 1
+#define SWB_ABI_VERSION 2
 
 enum { SWB_OK = 0, SWB_ERR_ARG = 1, SWB_ERR_CUDA = 2, SWB_ERR_STATE = 3, SWB_ERR_NOMEM = 4, SWB_ERR_NCCL = 5 };
 enum { SWB_F32 = 0, SWB_F64 = 1 };
@@ -49,6 +49,11 @@ enum {
 
 const char *swb_last_error(void);
 int32_t swb_abi_version(void);
+/* Layout of every struct that crosses this ABI, as the compiler that built the library sees it -- a JSON object
+ * {"<struct>": {"size": bytes, "fields": [["<member>", offset, size], ...]}, ...} in declaration order.  Bindings written in
+ * other languages (ext/SeismicWaves_B200BackendExt.jl, seismicwaves.jl_b200/_lib.py) are checked against it without needing
+ * their runtime (tests/test_julia_boundary.py).  Never fails; the string is static. */
+const char *swb_abi_layout(void);
 /* number of usable sm_100 devices (0 if none); never fails */
 int32_t swb_device_count(void);
 /* kernel launches issued by this process through the library so far (bench.py's gpu_launches) */
@@ -275,6 +280,18 @@ int32_t swb_sim_gradient_adjoint(swb_sim *sim, const void *host_adjsrc);
 /* same two phases with an identity-covariance L2 misfit evaluated on the device:
  * observed: host (nt, nrec[,2]) or NULL (= zeros).  misfit_out (may be NULL) receives dot(r, r)/2. */
 int32_t swb_sim_gradient_l2(swb_sim *sim, const void *host_observed, void *host_seismograms_or_null, double *misfit_out);
+
+/* The same with the windows and a diagonal inverse covariance of the reference's L2Misfit (src/inversion/misfits/L2Misfit.jl:24-95)
+ * applied on the device: r = syn - observed; r = mask .* r (windows, L2Misfit.jl:28-34); adjoint source = -(invcov_diag .* r)
+ * (= -∂χ_∂u for a Diagonal invcov, L2Misfit.jl:64-77); misfit = dot(r, invcov_diag .* r) / 2.  Host vectors of T with one entry per
+ * time sample; NULL = all ones (no window / identity covariance); observed NULL = zeros.  Dense covariances and other
+ * AbstractMisfits use swb_sim_gradient_forward / swb_sim_gradient_adjoint with the adjoint source computed by the caller. */
+typedef struct {
+    const void *observed;     /* host (nt, nrec) or (nt, 2, nrec) of T, or NULL */
+    const void *invcov_diag;  /* host (nt) of T, or NULL */
+    const void *mask;         /* host (nt) of T (0 / 1), or NULL */
+} swb_l2_spec;
+int32_t swb_sim_gradient_l2_ex(swb_sim *sim, const swb_l2_spec *spec, void *host_seismograms_or_null, double *misfit_out);
 
 /* Raw correlated fields of the last shot (what the reference downloads with Array(...)):
  *  SWB_ACOU_CD: 0 grad_vp;  SWB_ACOU_VD: 0 grad_m0, 1 grad_m1_stag[1], 2 grad_m1_stag[2];

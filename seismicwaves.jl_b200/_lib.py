@@ -101,16 +101,20 @@ class swb_sim_desc(C.Structure):
     ]
 
 
+class swb_l2_spec(C.Structure):
+    _fields_ = [("observed", C.c_void_p), ("invcov_diag", C.c_void_p), ("mask", C.c_void_p)]
+
+
 # every symbol include/swb200.h declares (tests check the header against this list and the .so against both)
 EXPORTS = [
-    "swb_last_error", "swb_abi_version", "swb_device_count", "swb_launch_count",
+    "swb_last_error", "swb_abi_version", "swb_abi_layout", "swb_device_count", "swb_launch_count",
     "swb_set_device", "swb_malloc", "swb_free", "swb_memcpy_h2d", "swb_memcpy_d2h", "swb_memcpy_d2d", "swb_fill", "swb_synchronize",
     "swb_acou_cd_forward_onestep", "swb_acou_cd_adjoint_onestep", "swb_acou_cd_correlate_gradient", "swb_prescale_residuals",
     "swb_acou_vd_forward_onestep", "swb_acou_vd_adjoint_onestep", "swb_acou_vd_correlate_gradient_m0", "swb_acou_vd_correlate_gradient_m1",
     "swb_ela_forward_onestep", "swb_ela_adjoint_onestep", "swb_ela_correlate_gradients",
     "swb_sim_create", "swb_sim_destroy", "swb_sim_device_bytes", "swb_sim_set_material", "swb_sim_set_material_device", "swb_sim_set_cpml",
     "swb_sim_bind_scalar_shot", "swb_sim_bind_elastic_shot", "swb_sim_forward", "swb_sim_get_snapshot",
-    "swb_sim_gradient_forward", "swb_sim_gradient_adjoint", "swb_sim_gradient_l2", "swb_sim_get_raw_gradient",
+    "swb_sim_gradient_forward", "swb_sim_gradient_adjoint", "swb_sim_gradient_l2", "swb_sim_gradient_l2_ex", "swb_sim_get_raw_gradient",
     "swb_sim_accumulate_gradient", "swb_sim_zero_total_gradient", "swb_sim_total_gradient_ptr", "swb_sim_get_total_gradient",
     "swb_sim_cell_updates", "swb_sim_get_field", "swb_sim_stream", "swb_sim_kernel_timing", "swb_sim_kernel_timing_class",
     "swb_comm_unique_id", "swb_comm_create", "swb_comm_destroy", "swb_comm_allreduce_sum", "swb_sim_allreduce_total_gradient", "swb_sim_set_slab",
@@ -132,6 +136,7 @@ def load() -> C.CDLL:
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     lib.swb_last_error.restype = C.c_char_p
     lib.swb_abi_version.restype = C.c_int32
+    lib.swb_abi_layout.restype = C.c_char_p
     lib.swb_device_count.restype = C.c_int32
     lib.swb_launch_count.restype = C.c_int64
     lib.swb_sim_device_bytes.restype = C.c_int64
@@ -171,6 +176,7 @@ def load() -> C.CDLL:
         "swb_sim_gradient_forward": [vp, vp],
         "swb_sim_gradient_adjoint": [vp, vp],
         "swb_sim_gradient_l2": [vp, vp, vp, C.POINTER(dbl)],
+        "swb_sim_gradient_l2_ex": [vp, C.POINTER(swb_l2_spec), vp, C.POINTER(dbl)],
         "swb_sim_get_raw_gradient": [vp, i32, vp],
         "swb_sim_accumulate_gradient": [vp, i64, vp, i32, i64, vp, i32],
         "swb_sim_zero_total_gradient": [vp],

@@ -231,9 +231,11 @@ class WaveSimulation:
         post-processed and accumulated on the device by accumulate_gradient()."""
         self._bind(shot)
         seis = shot.recs.seismograms
-        if isinstance(misfit, L2Misfit) and misfit._is_plain() and not getattr(self, "force_host_misfit", False):
-            obs = _as_T(misfit.observed, self.T)
-            _lib.check(self.lib.swb_sim_gradient_l2(self._h, _vp(obs), _vp(seis), None))
+        spec = misfit._device_spec(self.T) if isinstance(misfit, L2Misfit) and not getattr(self, "force_host_misfit", False) else None
+        if spec is not None:  # residual, windows, diagonal covariance on the device: no D2H / H2D round trip between the sweeps
+            obs, (w, mask) = _as_T(misfit.observed, self.T), spec
+            l2 = _lib.swb_l2_spec(obs.ctypes.data, None if w is None else w.ctypes.data, None if mask is None else mask.ctypes.data)
+            _lib.check(self.lib.swb_sim_gradient_l2_ex(self._h, C.byref(l2), _vp(seis), None))
         else:
             _lib.check(self.lib.swb_sim_gradient_forward(self._h, _vp(seis)))
             adjsrc = _as_T(-misfit.dchi_du(shot.recs), self.T)

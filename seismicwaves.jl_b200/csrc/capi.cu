@@ -212,6 +212,66 @@ int32_t swb_ela_correlate_gradients(const swb_ela_correlate_args *a)
 }
 
 // ---- 3. per-shot engine -----------------------------------------------------------------------------
+// ---- ABI layout report ---------------------------------------------------------------------------------------------------
+namespace {
+struct LayoutWriter {
+    std::string s = "{";
+    bool first_struct = true, first_field = true;
+    void begin(const char *name, size_t size)
+    {
+        s += std::string(first_struct ? "" : ", ") + "\"" + name + "\": {\"size\": " + std::to_string(size) + ", \"fields\": [";
+        first_struct = false;
+        first_field = true;
+    }
+    void field(const char *name, size_t off, size_t size)
+    {
+        s += std::string(first_field ? "" : ", ") + "[\"" + name + "\", " + std::to_string(off) + ", " + std::to_string(size) + "]";
+        first_field = false;
+    }
+    void end() { s += "]}"; }
+};
+#define SWB_L_BEGIN(S) { typedef S cur_t; w.begin(#S, sizeof(S));
+#define SWB_L_F(m) w.field(#m, offsetof(cur_t, m), sizeof(((cur_t *)nullptr)->m));
+#define SWB_L_END w.end(); }
+std::string build_layout()
+{
+    LayoutWriter w;
+    SWB_L_BEGIN(swb_cpml_axis) SWB_L_F(a) SWB_L_F(a_h) SWB_L_F(b) SWB_L_F(b_h) SWB_L_END
+    SWB_L_BEGIN(swb_points) SWB_L_F(n) SWB_L_F(pos) SWB_L_F(tf) SWB_L_F(nt) SWB_L_END
+    SWB_L_BEGIN(swb_acou_cd_step_args)
+    SWB_L_F(dtype) SWB_L_F(ndim) SWB_L_F(halo) SWB_L_F(flags) SWB_L_F(n) SWB_L_F(spacing) SWB_L_F(pold) SWB_L_F(pcur) SWB_L_F(pnew) SWB_L_F(fact) SWB_L_F(psi) SWB_L_F(xi)
+    SWB_L_F(cpml) SWB_L_F(src) SWB_L_F(rec) SWB_L_F(it) SWB_L_F(stream) SWB_L_END
+    SWB_L_BEGIN(swb_acou_vd_step_args)
+    SWB_L_F(dtype) SWB_L_F(halo) SWB_L_F(flags) SWB_L_F(_pad) SWB_L_F(n) SWB_L_F(spacing) SWB_L_F(pcur) SWB_L_F(vcur) SWB_L_F(fact_m0) SWB_L_F(fact_m1_stag) SWB_L_F(psi)
+    SWB_L_F(xi) SWB_L_F(cpml) SWB_L_F(src) SWB_L_F(rec) SWB_L_F(it) SWB_L_F(stream) SWB_L_END
+    SWB_L_BEGIN(swb_sinc_points) SWB_L_F(n) SWB_L_F(off) SWB_L_F(ij) SWB_L_F(coef) SWB_L_END
+    SWB_L_BEGIN(swb_ela_step_args)
+    SWB_L_F(dtype) SWB_L_F(halo) SWB_L_F(flags) SWB_L_F(freetop) SWB_L_F(n) SWB_L_F(spacing) SWB_L_F(dt) SWB_L_F(uold) SWB_L_F(ucur) SWB_L_F(unew) SWB_L_F(sigma)
+    SWB_L_F(lambda) SWB_L_F(mu) SWB_L_F(rho_ihalf) SWB_L_F(rho_jhalf) SWB_L_F(mu_ihalf_jhalf) SWB_L_F(psi_dsdx) SWB_L_F(psi_dsdz) SWB_L_F(psi_dudx) SWB_L_F(psi_dudz)
+    SWB_L_F(cpml) SWB_L_F(src_kind) SWB_L_F(_pad) SWB_L_F(src_pts) SWB_L_F(srctf) SWB_L_F(nt_tf) SWB_L_F(Mxx) SWB_L_F(Mzz) SWB_L_F(Mxz) SWB_L_F(rec_pts) SWB_L_F(traces)
+    SWB_L_F(nt_tr) SWB_L_F(it) SWB_L_F(stream) SWB_L_END
+    SWB_L_BEGIN(swb_ela_correlate_args)
+    SWB_L_F(dtype) SWB_L_F(flags) SWB_L_F(freetop) SWB_L_F(_pad) SWB_L_F(n) SWB_L_F(spacing) SWB_L_F(dt) SWB_L_F(adjucur) SWB_L_F(u_itm2) SWB_L_F(u_itm1) SWB_L_F(u_it)
+    SWB_L_F(lambda) SWB_L_F(mu) SWB_L_F(grad_rho_ihalf) SWB_L_F(grad_rho_jhalf) SWB_L_F(grad_lambda) SWB_L_F(grad_mu) SWB_L_F(grad_mu_ihalf_jhalf) SWB_L_F(stream) SWB_L_END
+    SWB_L_BEGIN(swb_sim_desc)
+    SWB_L_F(kind) SWB_L_F(dtype) SWB_L_F(ndim) SWB_L_F(device) SWB_L_F(n) SWB_L_F(spacing) SWB_L_F(dt) SWB_L_F(nt) SWB_L_F(halo) SWB_L_F(freetop) SWB_L_F(gradient)
+    SWB_L_F(check_freq) SWB_L_F(flags) SWB_L_F(_pad) SWB_L_END
+    SWB_L_BEGIN(swb_sinc_points_host) SWB_L_F(n) SWB_L_F(off) SWB_L_F(ij) SWB_L_F(coef) SWB_L_END
+    SWB_L_BEGIN(swb_l2_spec) SWB_L_F(observed) SWB_L_F(invcov_diag) SWB_L_F(mask) SWB_L_END
+    w.s += "}";
+    return w.s;
+}
+#undef SWB_L_BEGIN
+#undef SWB_L_F
+#undef SWB_L_END
+} // namespace
+
+const char *swb_abi_layout(void)
+{
+    static const std::string layout = build_layout();
+    return layout.c_str();
+}
+
 int32_t swb_sim_create(const swb_sim_desc *desc, swb_sim **sim)
 {
     SWB_API_BEGIN
@@ -279,7 +339,12 @@ int32_t swb_sim_gradient_forward(swb_sim *sim, void *host_seismograms) { SIM_CAL
 int32_t swb_sim_gradient_adjoint(swb_sim *sim, const void *host_adjsrc) { SIM_CALL(sim->impl->gradient_adjoint(host_adjsrc)) }
 int32_t swb_sim_gradient_l2(swb_sim *sim, const void *host_observed, void *host_seismograms_or_null, double *misfit_out)
 {
-    SIM_CALL(sim->impl->gradient_l2(host_observed, host_seismograms_or_null, misfit_out))
+    swb_l2_spec spec = {host_observed, nullptr, nullptr};
+    SIM_CALL(sim->impl->gradient_l2(spec, host_seismograms_or_null, misfit_out))
+}
+int32_t swb_sim_gradient_l2_ex(swb_sim *sim, const swb_l2_spec *spec, void *host_seismograms_or_null, double *misfit_out)
+{
+    SIM_CALL(SWB_REQUIRE(spec != nullptr, "null L2 spec"); sim->impl->gradient_l2(*spec, host_seismograms_or_null, misfit_out))
 }
 int32_t swb_sim_get_raw_gradient(swb_sim *sim, int32_t which, void *host_out) { SIM_CALL(sim->impl->get_raw_gradient(which, host_out)) }
 int32_t swb_sim_accumulate_gradient(swb_sim *sim, int64_t nsrcpos, const void *src_positions, int32_t mute_radius_src, int64_t nrecpos,

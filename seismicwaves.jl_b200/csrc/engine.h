@@ -114,13 +114,16 @@ class SimBase {
     virtual void forward(void *host_seis, int snapevery) = 0;
     virtual void gradient_forward(void *host_seis) = 0;
     virtual void gradient_adjoint(const void *host_adjsrc) = 0;
-    virtual void gradient_l2(const void *host_obs, void *host_seis, double *misfit) = 0;
+    // forward sweep -> residual, window, diagonal covariance and misfit on the device -> adjoint sweep (L2Misfit.jl:24-95)
+    void gradient_l2(const swb_l2_spec &spec, void *host_seis, double *misfit);
     virtual void get_raw_gradient(int which, void *host_out) = 0;
     virtual void accumulate_gradient(int64_t nsrcpos, const void *srcpos, int rs, int64_t nrecpos, const void *recpos, int rr) = 0;
     virtual int n_total_gradients() const = 0;
     virtual void get_field(const std::string &name, void *host_out, size_t nbytes) = 0;
     // z-slab domain decomposition (forward only): this sim holds one slab of the last axis, ghost planes included; a negative
     // neighbour rank marks a true domain end
+    // the adjoint loop of swgradient_1shot! on the adjoint source in adjsrc_ (after gradient_forward)
+    virtual void adjoint_loop() = 0;
     virtual void set_slab(swb_comm *, int, int) { throw Error(SWB_ERR_ARG, "z-slab decomposition is available for the fused 3D acoustic constant-density engine only"); }
     void zero_total_gradient();
     void total_gradient_ptr(int which, void **p, size_t *nelem);
@@ -165,6 +168,7 @@ class SimBase {
     bool cpml_lo_inactive_[3] = {false, false, false};
     // acoustic shot binding
     DevBuf possrc_, posrec_, srctf_, traces_, adjsrc_;
+    DevBuf l2_obs_, l2_w_, l2_mask_, l2_acc_; // device-side L2 misfit: observed data, per-sample weights, window mask, accumulator
     int64_t nsrc_ = 0, nrec_ = 0;
     bool shot_bound_ = false;
     bool fwd_done_ = false;

@@ -103,24 +103,6 @@ class AcousticCD : public SimBase {
         adjoint_loop();
     }
 
-    void gradient_l2(const void *host_obs, void *host_seis, double *misfit) override
-    {
-        gradient_forward(host_seis);
-        const size_t ntr = (size_t)desc.nt * nrec_;
-        void *obs = nullptr;
-        if (host_obs) { // observed data staged in the (not yet used) adjoint-source buffer's twin
-            ensure(obs_, adjsrc_.bytes);
-            upload(obs_.p, host_obs, obs_.bytes);
-            obs = obs_.p;
-        }
-        SWB_CUDA(cudaMemsetAsync(misfit_acc_.p, 0, sizeof(double), stream));
-        post_l2_adjsrc(desc.dtype, ntr, traces_.p, obs, adjsrc_.p, misfit_acc_.as<double>(), stream);
-        adjoint_loop();
-        if (misfit) {
-            download(misfit, misfit_acc_.p, sizeof(double));
-        }
-    }
-
     void get_raw_gradient(int which, void *host_out) override
     {
         use_device();
@@ -462,22 +444,6 @@ class AcousticVD : public SimBase {
         use_device();
         upload(adjsrc_.p, host_adjsrc, adjsrc_.bytes);
         adjoint_loop();
-    }
-
-    void gradient_l2(const void *host_obs, void *host_seis, double *misfit) override
-    {
-        gradient_forward(host_seis);
-        void *obs = nullptr;
-        if (host_obs) {
-            ensure(obs_, adjsrc_.bytes);
-            upload(obs_.p, host_obs, obs_.bytes);
-            obs = obs_.p;
-        }
-        SWB_CUDA(cudaMemsetAsync(misfit_acc_.p, 0, sizeof(double), stream));
-        post_l2_adjsrc(desc.dtype, (size_t)desc.nt * nrec_, traces_.p, obs, adjsrc_.p, misfit_acc_.as<double>(), stream);
-        adjoint_loop();
-        if (misfit)
-            download(misfit, misfit_acc_.p, sizeof(double));
     }
 
     void get_raw_gradient(int which, void *host_out) override

@@ -366,6 +366,35 @@ void SimBase::set_cpml(int axis, const void *a, const void *a_h, const void *b, 
     cpml_changed(axis);
 }
 
+void SimBase::gradient_l2(const swb_l2_spec &spec, void *host_seis, double *misfit)
+{
+    gradient_forward(host_seis);
+    SWB_REQUIRE(adjsrc_.bytes > 0 && adjsrc_.bytes == traces_.bytes, "no gradient shot bound");
+    const size_t nt = (size_t)desc.nt, n = adjsrc_.bytes / esize;
+    const void *obs = nullptr, *w = nullptr, *mask = nullptr;
+    if (spec.observed) {
+        ensure(l2_obs_, adjsrc_.bytes);
+        upload(l2_obs_.p, spec.observed, l2_obs_.bytes);
+        obs = l2_obs_.p;
+    }
+    if (spec.invcov_diag) {
+        ensure(l2_w_, esize * nt);
+        upload(l2_w_.p, spec.invcov_diag, l2_w_.bytes);
+        w = l2_w_.p;
+    }
+    if (spec.mask) {
+        ensure(l2_mask_, esize * nt);
+        upload(l2_mask_.p, spec.mask, l2_mask_.bytes);
+        mask = l2_mask_.p;
+    }
+    ensure(l2_acc_, sizeof(double));
+    SWB_CUDA(cudaMemsetAsync(l2_acc_.p, 0, sizeof(double), stream));
+    post_l2_adjsrc(desc.dtype, n, nt, traces_.p, obs, w, mask, adjsrc_.p, l2_acc_.as<double>(), stream);
+    adjoint_loop();
+    if (misfit)
+        download(misfit, l2_acc_.p, sizeof(double));
+}
+
 swb_cpml_axis SimBase::cpml_axis(int ax) const
 {
     swb_cpml_axis c;

@@ -133,6 +133,31 @@ class ElasticIso : public SimBase {
     {
         SWB_REQUIRE(desc.gradient, "simulation was not built with gradient=true");
         begin_shot();
+        gradient_forward_body(host_seis);
+    }
+
+    // dense wavefield state, adjoint state and checkpoint storage of the step-by-step path, for a subclass that normally keeps its own
+    void ensure_unfused_state()
+    {
+        if (!fw_ready_) {
+            alloc_state(fw_);
+            fw_ready_ = true;
+        }
+        if (desc.gradient && !ckpt_) {
+            alloc_state(ad_);
+            std::vector<DeviceCheckpointer::FieldSpec> fs(5);
+            fs[0].comp_bytes = {nbx_, nbz_};
+            fs[0].width = 2;
+            fs[0].buffered = true; // "ucur"
+            for (int gq = 0; gq < 4; ++gq)
+                fs[1 + gq].comp_bytes = {psib_[gq][0], psib_[gq][1]};
+            ckpt_.reset(new DeviceCheckpointer(desc.nt, desc.check_freq, fs, stream));
+            dev_bytes_ += (int64_t)ckpt_->bytes();
+        }
+    }
+
+    void gradient_forward_body(void *host_seis)
+    {
         ckpt_->reset();
         for (int64_t it = 1; it <= desc.nt; ++it) {
             step(fw_, false, it, true);
@@ -149,22 +174,6 @@ class ElasticIso : public SimBase {
         use_device();
         upload(adjsrc_.p, host_adjsrc, adjsrc_.bytes);
         adjoint_loop();
-    }
-
-    void gradient_l2(const void *host_obs, void *host_seis, double *misfit) override
-    {
-        gradient_forward(host_seis);
-        void *obs = nullptr;
-        if (host_obs) {
-            ensure(obs_, adjsrc_.bytes);
-            upload(obs_.p, host_obs, obs_.bytes);
-            obs = obs_.p;
-        }
-        SWB_CUDA(cudaMemsetAsync(misfit_acc_.p, 0, sizeof(double), stream));
-        post_l2_adjsrc(desc.dtype, (size_t)desc.nt * 2 * nrec_, traces_.p, obs, adjsrc_.p, misfit_acc_.as<double>(), stream);
-        adjoint_loop();
-        if (misfit)
-            download(misfit, misfit_acc_.p, sizeof(double));
     }
 
     void get_raw_gradient(int which, void *host_out) override

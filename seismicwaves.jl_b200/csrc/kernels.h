@@ -32,7 +32,8 @@ void post_vd_chain_accumulate(int dtype, size_t n, const void *g0, const void *g
 void post_ela_props(int dtype, const int64_t *n, const void *rho, const void *mu, int interp_rho, int interp_mu, void *rho_ih, void *rho_jh, void *mu_hh, cudaStream_t st);
 void post_ela_backinterp(int dtype, const int64_t *n, const void *rho, const void *mu, int interp_rho, int interp_mu, const void *g_ri, const void *g_rj,
                          const void *g_mh, const void *g_mu, void *out_rho, void *out_mu, cudaStream_t st);
-void post_l2_adjsrc(int dtype, size_t n, const void *syn, const void *obs_or_null, void *adjsrc, double *misfit_accum, cudaStream_t st);
+void post_l2_adjsrc(int dtype, size_t n, size_t nt, const void *syn, const void *obs_or_null, const void *w_or_null, const void *mask_or_null, void *adjsrc,
+                    double *misfit_accum, cudaStream_t st);
 void post_axpy(int dtype, size_t n, const void *x, void *y, cudaStream_t st); // y += x
 
 } // namespace swb

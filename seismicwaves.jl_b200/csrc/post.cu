@@ -421,24 +421,29 @@ void post_ela_backinterp(int dtype, const int64_t *n, const void *rho, const voi
     count_launch();
 }
 
-// L2 misfit with identity covariance on the device (L2Misfit.jl:24-77): r = syn - obs;
-// adjsrc = -r ; misfit += dot(r, r)/2 (accumulated in double)
+// L2 misfit on the device (L2Misfit.jl:24-95) for an identity or Diagonal inverse covariance and optional windows:
+//   r = syn - obs;  r = mask .* r (if windows);  adjsrc = -(w .* r) (= -invcov * r);  misfit += dot(r, w .* r)/2 (accumulated in double)
+// w, mask: one entry per time sample (the fastest index of syn); NULL = ones.
 template <class T>
-__global__ void l2_adjsrc_kernel(const T *syn, const T *obs, T *adj, double *acc, size_t n)
+__global__ void l2_adjsrc_kernel(const T *syn, const T *obs, const T *w, const T *mask, T *adj, double *acc, size_t n, size_t nt)
 {
     double local = 0.0;
     GRID_STRIDE(q, n)
     {
-        const T r = obs ? syn[q] - obs[q] : syn[q];
-        adj[q] = -r;
-        local += (double)r * (double)r;
+        T r = obs ? syn[q] - obs[q] : syn[q];
+        const size_t t = q % nt;
+        if (mask)
+            r = mask[t] * r;
+        const T wr = w ? w[t] * r : r;
+        adj[q] = -wr;
+        local += (double)r * (double)wr;
     }
     for (int o = 16; o > 0; o >>= 1)
         local += __shfl_down_sync(0xffffffffu, local, o);
     __shared__ double sm[8];
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int wp = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (l == 0)
-        sm[w] = local;
+        sm[wp] = local;
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0;
@@ -448,14 +453,14 @@ __global__ void l2_adjsrc_kernel(const T *syn, const T *obs, T *adj, double *acc
     }
 }
 
-void post_l2_adjsrc(int dtype, size_t n, const void *syn, const void *obs, void *adj, double *acc, cudaStream_t st)
+void post_l2_adjsrc(int dtype, size_t n, size_t nt, const void *syn, const void *obs, const void *w, const void *mask, void *adj, double *acc, cudaStream_t st)
 {
     if (n == 0)
         return;
     if (dtype == SWB_F64)
-        l2_adjsrc_kernel<double><<<grid1d(n), 256, 0, st>>>((const double *)syn, (const double *)obs, (double *)adj, acc, n);
+        l2_adjsrc_kernel<double><<<grid1d(n), 256, 0, st>>>((const double *)syn, (const double *)obs, (const double *)w, (const double *)mask, (double *)adj, acc, n, nt);
     else
-        l2_adjsrc_kernel<float><<<grid1d(n), 256, 0, st>>>((const float *)syn, (const float *)obs, (float *)adj, acc, n);
+        l2_adjsrc_kernel<float><<<grid1d(n), 256, 0, st>>>((const float *)syn, (const float *)obs, (const float *)w, (const float *)mask, (float *)adj, acc, n, nt);
     check_launch("l2_adjsrc");
     count_launch();
 }

@@ -255,6 +255,26 @@ class L2Misfit:
             return bool(np.all(ic == 1))
         return bool(np.array_equal(ic, np.eye(ic.shape[0], dtype=ic.dtype)))
 
+    def _device_spec(self, T):
+        """(invcov_diag or None, mask or None) if the misfit can be evaluated by the engine (identity / diagonal inverse covariance,
+        any windows: swb_sim_gradient_l2_ex), else None (dense covariance -> host path)."""
+        ic = self.invcov
+        w = None
+        if ic is not None:
+            if ic.ndim == 1:
+                w = ic
+            elif np.array_equal(ic, np.diag(np.diag(ic))):
+                w = np.diag(ic)
+            else:
+                return None
+            w = None if bool(np.all(w == 1)) else np.ascontiguousarray(w, dtype=T)
+        mask = None
+        if self.windows:
+            mask = np.zeros(self.observed.shape[0], dtype=T)
+            for (a, b) in self.windows:
+                mask[a - 1:b] = 1
+        return w, mask
+
     def _residuals(self, seis: np.ndarray) -> np.ndarray:
         res = (seis - self.observed).astype(seis.dtype)
         if self.windows:

@@ -234,3 +234,36 @@ def test_eager_launches_equal_graph_replay(kind):
     for k in ga:
         assert np.array_equal(ga[k], gb[k]), k
     assert ma == mb
+
+
+def test_moment_tensor_source_near_the_edge_falls_back_to_the_step_by_step_path():
+    """A sinc-spread moment-tensor source within a few cells of a lateral edge touches stress cells the reference never updates
+    (they accumulate the injection, elastic2D_iso_xPU.jl:187-199).  The fused engine cannot keep such a stress on chip: the shot is
+    run on the four-sweep path automatically (no error, no flag), and the next ordinary shot is fused again."""
+    import swb200 as S
+
+    case = elastic_case(n=(72, 64), nt=110, halo=6, dtype=np.float64, kind="momten", nshots=2, nrec=4, seed=31)
+    h = case["h"]
+    case["shots"][0]["src_positions"][:, 0] = (case["n"][0] - 3) * h + 0.31 * h   # 2.7 cells from the right edge: the sinc stencil reaches column nx
+    case["shots"][0]["src_positions"][:, 1] = 0.55 * (case["n"][1] - 1) * h
+    ref, _ = oracle_forward(case)
+    params, matprop, shots, _, runparams, _ = product_inputs(case)
+    ws = S.build_wavesim(params, matprop, runparams=runparams)
+    l0 = S._lib.load().swb_launch_count()
+    S.swforward(ws, matprop, shots[:1])
+    l1 = S._lib.load().swb_launch_count()
+    S.swforward(ws, matprop, shots[1:])
+    l2 = S._lib.load().swb_launch_count()
+    ws.close()
+    for r, sh in zip(ref, shots):
+        assert np.max(np.abs(r)) > 0
+        assert rel_l2(sh.recs.seismograms, r) <= 1e-12
+    assert (l1 - l0) >= 3 * case["nt"] > (l2 - l1)   # four-sweep path (>= 3 launches per step) vs fused path
+    # the gradient of the near-edge shot takes the same route
+    obs = make_observed(case, ref)
+    (gref, mref), _ = oracle_gradient(case, obs, check_freq=7, mute_src=2)
+    params, matprop, shots, misfit, runparams, gradparams = product_inputs(case, observed=obs, check_freq=7, mute_src=2)
+    ggot, mgot = S.swgradient(params, matprop, shots, misfit, runparams=runparams, gradparams=gradparams)
+    for k in gref:
+        assert rel_l2(ggot[k], gref[k]) <= 1e-10, k
+    assert abs(float(mgot) - float(mref)) <= 1e-10 * abs(float(mref))
