@@ -22,7 +22,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert sorted(S._lib.EXPORTS) == declared
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.swb_abi_version() == 1
+    assert lib.swb_abi_version() == 2  # SWB_ABI_VERSION of include/swb200.h (2: swb_abi_layout, swb_sim_gradient_l2_ex)
 
 
 def test_no_cpu_fallback_without_device():
