@@ -173,7 +173,28 @@ class SimBase {
     bool shot_bound_ = false;
     bool fwd_done_ = false;
     std::vector<DevBuf> total_grad_;
-    std::map<int64_t, std::vector<std::vector<char>>> snapshots_; // it -> field components on the host
+    std::map<int64_t, std::vector<std::vector<char>>> snapshots_; // it -> field components on the host (step-by-step engines)
+    // Snapshots of the fused engines (savesnapshot!, src/utils/snapshotter.jl:33-41) without leaving the graph-captured time loop: a snapshot
+    // step copies the dense fields into a device-resident slot (device to device, inside the sweep), and a side stream drains the slots to
+    // pinned host memory while the sweep goes on; the two streams join at the end of the sweep.
+    struct SnapStore {
+        int snapevery = 0;
+        int64_t nsnap = 0;
+        std::vector<size_t> comp_off; // byte offset of each component inside a slot (+ total at the end)
+        std::vector<size_t> comp_bytes;
+        DevBuf dev;
+        PinnedBuf host;
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+        bool used = false; // a drain was enqueued in the current sweep
+    } snap_;
+    // (re)sizes the store; returns true when a pointer changed (captured graphs must be dropped).  false + !snap_fits() when the store
+    // would not fit the device-memory budget: the caller then takes snapshots the slow way
+    bool snap_setup(int snapevery, const std::vector<size_t> &comp_bytes);
+    bool snap_ok_ = false;
+    void *snap_dev(int64_t it, int comp) const; // where component `comp` of the snapshot of step `it` goes (dense, device)
+    void snap_drain(int64_t it);                // enqueue slot -> pinned host on the side stream (after everything enqueued so far)
+    void snap_finish();                         // join the side stream back into the sim's stream
     PinnedBuf pin_;
     int64_t dev_bytes_ = 0;
     bool timing_ = false, tsampled_ = false;

@@ -287,6 +287,12 @@ SimBase::~SimBase()
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
+    if (snap_.st) {
+        cudaStreamSynchronize(snap_.st);
+        cudaStreamDestroy(snap_.st);
+        cudaEventDestroy(snap_.ev_fork);
+        cudaEventDestroy(snap_.ev_join);
+    }
 }
 
 DevBuf SimBase::dalloc(size_t bytes)
@@ -460,8 +466,75 @@ void SimBase::get_total_gradient(int which, void *host_out)
     download(host_out, total_grad_[which].p, total_grad_[which].bytes);
 }
 
+bool SimBase::snap_setup(int snapevery, const std::vector<size_t> &comp_bytes)
+{
+    use_device();
+    snap_ok_ = false;
+    if (snapevery <= 0)
+        return false;
+    std::vector<size_t> off(comp_bytes.size() + 1, 0);
+    for (size_t c = 0; c < comp_bytes.size(); ++c)
+        off[c + 1] = off[c] + (comp_bytes[c] + 255) / 256 * 256;
+    const int64_t nsnap = desc.nt / snapevery;
+    const size_t total = off.back() * (size_t)std::max<int64_t>(nsnap, 1);
+    size_t free_b = 0, total_b = 0;
+    SWB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (total > snap_.dev.bytes && total - snap_.dev.bytes > free_b / 2) // keep half of what is left for the caller: fall back
+        return false;
+    if (!snap_.st) {
+        SWB_CUDA(cudaStreamCreateWithFlags(&snap_.st, cudaStreamNonBlocking));
+        SWB_CUDA(cudaEventCreateWithFlags(&snap_.ev_fork, cudaEventDisableTiming));
+        SWB_CUDA(cudaEventCreateWithFlags(&snap_.ev_join, cudaEventDisableTiming));
+    }
+    bool ch = snapevery != snap_.snapevery || off != snap_.comp_off;
+    snap_.snapevery = snapevery;
+    snap_.nsnap = nsnap;
+    snap_.comp_off = off;
+    snap_.comp_bytes = comp_bytes;
+    ch |= ensure(snap_.dev, total);
+    if (total > snap_.host.bytes) {
+        snap_.host.ensure(total);
+        ch = true;
+    }
+    snap_ok_ = true;
+    return ch;
+}
+
+void *SimBase::snap_dev(int64_t it, int comp) const
+{
+    const int64_t s = it / snap_.snapevery - 1;
+    SWB_REQUIRE(snap_ok_ && it % snap_.snapevery == 0 && s >= 0 && s < snap_.nsnap && comp >= 0 && comp + 1 < (int)snap_.comp_off.size(), "snapshot slot out of range");
+    return (char *)snap_.dev.p + (size_t)s * snap_.comp_off.back() + snap_.comp_off[comp];
+}
+
+void SimBase::snap_drain(int64_t it)
+{
+    const size_t slot = snap_.comp_off.back(), o = (size_t)(it / snap_.snapevery - 1) * slot;
+    SWB_CUDA(cudaEventRecord(snap_.ev_fork, stream));
+    SWB_CUDA(cudaStreamWaitEvent(snap_.st, snap_.ev_fork, 0));
+    SWB_CUDA(cudaMemcpyAsync((char *)snap_.host.p + o, (const char *)snap_.dev.p + o, slot, cudaMemcpyDeviceToHost, snap_.st));
+    snap_.used = true;
+}
+
+void SimBase::snap_finish()
+{
+    if (!snap_.used)
+        return;
+    SWB_CUDA(cudaEventRecord(snap_.ev_join, snap_.st));
+    SWB_CUDA(cudaStreamWaitEvent(stream, snap_.ev_join, 0));
+    snap_.used = false;
+}
+
 void SimBase::get_snapshot(int64_t it, int field, void *host_out)
 {
+    if (snap_ok_ && snap_.snapevery > 0 && snapshots_.empty()) { // taken by a fused engine: pinned slots, complete once the sweep's stream is
+        SWB_REQUIRE(it >= 1 && it % snap_.snapevery == 0 && it / snap_.snapevery <= snap_.nsnap, "no snapshot stored for this time step");
+        SWB_REQUIRE(field >= 0 && field + 1 < (int)snap_.comp_off.size(), "snapshot field out of range");
+        sync();
+        const size_t o = (size_t)(it / snap_.snapevery - 1) * snap_.comp_off.back() + snap_.comp_off[field];
+        std::memcpy(host_out, (const char *)snap_.host.p + o, snap_.comp_bytes[field]);
+        return;
+    }
     auto s = snapshots_.find(it);
     SWB_REQUIRE(s != snapshots_.end(), "no snapshot stored for this time step");
     SWB_REQUIRE(field >= 0 && field < (int)s->second.size(), "snapshot field out of range");

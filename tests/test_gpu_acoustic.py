@@ -347,3 +347,34 @@ def test_eager_launches_equal_graph_replay(kind, n):
     for k in ga:
         assert np.array_equal(ga[k], gb[k]), k
     assert ma == mb
+
+
+@pytest.mark.parametrize("kind,n", [("acoustic_cd", (61, 53)), ("acoustic_cd", (30, 26, 28)), ("acoustic_vd", (67, 59))])
+def test_snapshots_from_the_graph_captured_sweep(kind, n):
+    """savesnapshot! (snapshotter.jl:33-41) inside the CUDA-graph replay: device-resident slots drained to pinned host memory on a side
+    stream.  Same fields as the oracle's snapshots, bit-identical to the eager (no-graph) path, unchanged seismograms, and a second shot
+    replays the captured sweep into the same slots."""
+    import swb200 as S
+
+    nt = 60 if len(n) == 2 else 40
+    case = acoustic_case(kind=kind, n=n, nt=nt, halo=5, dtype=np.float32, seed=8, nshots=2)
+    ref_seis, snaps_ref = oracle_forward(case, snapevery=10)
+    params, matprop, shots, _, runparams, _ = product_inputs(case, snapevery=10)
+    ws = S.build_wavesim(params, matprop, runparams=runparams)
+    snaps = S.swforward(ws, matprop, shots)
+    ws.close()
+    seis_plain, _ = _forward_product(case)
+    _, snaps_eager = _forward_product(case, snapevery=10, graphs=False)
+    assert len(snaps) == 2
+    for s in range(2):
+        assert sorted(snaps[s].keys()) == list(range(10, nt + 1, 10))
+        assert np.array_equal(shots[s].recs.seismograms, seis_plain[s])
+        for it in snaps[s]:
+            assert np.max(np.abs(snaps[s][it]["pcur"])) > 0
+            assert rel_l2(snaps[s][it]["pcur"], snaps_ref[s][it]) <= 1e-6
+            assert np.array_equal(snaps[s][it]["pcur"], snaps_eager[s][it]["pcur"])
+            if kind == "acoustic_vd":
+                for c in range(2):
+                    assert np.max(np.abs(snaps[s][it]["vcur"][c])) > 0
+                    assert np.array_equal(snaps[s][it]["vcur"][c], snaps_eager[s][it]["vcur"][c])
+    assert not np.array_equal(snaps[0][nt]["pcur"], snaps[1][nt]["pcur"])  # the second shot really overwrote the slots
