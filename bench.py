@@ -608,6 +608,11 @@ def other_configs(peak):
 
 
 def main():
+    import faulthandler
+
+    faulthandler.enable()  # a fatal signal in a native library leaves a traceback on stderr instead of a silent exit
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION prints a banner on stdout, in front of the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
