@@ -199,6 +199,7 @@ struct L2Spec                  # swb_l2_spec
 end
 
 pad3(t::NTuple{N, T}, z) where {N, T} = ntuple(i -> i <= N ? t[i] : z, 3)
+pad2(t::NTuple{N, T}, z) where {N, T} = ntuple(i -> i <= N ? t[i] : z, 2)
 vptr(a::B200Array) = materialize!(a).ptr
 vptr(::Nothing) = C_NULL
 cpmlaxis(c) = CpmlAxis(vptr(c.a), vptr(c.a_h), vptr(c.b), vptr(c.b_h))
@@ -261,9 +262,10 @@ function acou_vd_args(model, possrcs, srctf, posrecs, traces, it, pname, vname, 
     v, m1, ψ, ξ = g.fields[vname].value, g.fields["fact_m1_stag"].value, g.fields[ψname].value, g.fields[ξname].value
     src = Points(size(possrcs, 1), vptr(possrcs), vptr(srctf), size(srctf, 1))
     rec = traces === nothing ? NOPOINTS : Points(size(posrecs, 1), vptr(posrecs), vptr(traces), size(traces, 1))
-    return AcouVDStepArgs(dtype_code(T), model.cpmlparams.halo, FLAGS[], 0, Tuple(Int64.(g.size)), Tuple(Float64.(g.spacing)),
-        vptr(g.fields[pname].value), Tuple(vptr.(v)), vptr(g.fields["fact_m0"].value), Tuple(vptr.(m1)), Tuple(vptr.(ψ)), Tuple(vptr.(ξ)),
-        Tuple(cpmlaxis.(model.cpmlcoeffs)), src, rec, it, C_NULL)
+    # a 1D simulation (acoustic1D_VD_xPU.jl) is the single-row case of the same entry point: n = (nx, 1), no y arrays
+    return AcouVDStepArgs(dtype_code(T), model.cpmlparams.halo, FLAGS[], 0, pad2(Tuple(Int64.(g.size)), Int64(1)), pad2(Tuple(Float64.(g.spacing)), 0.0),
+        vptr(g.fields[pname].value), pad2(Tuple(vptr.(v)), C_NULL), vptr(g.fields["fact_m0"].value), pad2(Tuple(vptr.(m1)), C_NULL),
+        pad2(Tuple(vptr.(ψ)), C_NULL), pad2(Tuple(vptr.(ξ)), C_NULL), pad2(Tuple(cpmlaxis.(model.cpmlcoeffs)), NOAXIS), src, rec, it, C_NULL)
 end
 function vd_forward_onestep_CPML!(model, possrcs, srctf, posrecs, traces, it; save_trace=true)
     args = acou_vd_args(model, possrcs, srctf, save_trace ? posrecs : nothing, save_trace ? traces : nothing, it, "pcur", "vcur", "ψ", "ξ")
@@ -277,9 +279,10 @@ function correlate_gradient_m0!(grad_m0::B200Array{T}, adjp, p_it, p_itm1, dt) w
     check(ccall((:swb_acou_vd_correlate_gradient_m0, lib), Int32, (Int32, Int32, Csize_t, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}),
         dtype_code(T), FLAGS[], length(grad_m0), vptr(grad_m0), vptr(adjp), vptr(p_it), vptr(p_itm1), Float64(dt), C_NULL))
 end
-function correlate_gradient_m1!(grad_m1_stag, adjv, p_it::B200Array{T, 2}, spacing) where {T}
-    n, sp = collect(Int64, size(p_it)), collect(Float64, spacing)
-    g, av = [vptr(x) for x in grad_m1_stag], [vptr(x) for x in adjv]
+function correlate_gradient_m1!(grad_m1_stag, adjv, p_it::B200Array{T, N}, spacing) where {T, N}
+    n, sp = collect(Int64, pad2(size(p_it), 1)), collect(Float64, pad2(Tuple(spacing), 0.0))   # 1D: n = (nx, 1), range (2:nx-2) inside the library
+    g, av = Ptr{Cvoid}[vptr(x) for x in grad_m1_stag], Ptr{Cvoid}[vptr(x) for x in adjv]
+    N == 1 && (push!(g, C_NULL); push!(av, C_NULL))
     check(ccall((:swb_acou_vd_correlate_gradient_m1, lib), Int32, (Int32, Int32, Ptr{Int64}, Ptr{Cdouble}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Cvoid}),
         dtype_code(T), FLAGS[], n, sp, g, av, vptr(p_it), C_NULL))
 end
@@ -369,12 +372,16 @@ end
 const Acoustic2D_CD_CPML_B200 = (; Data, zeros, ones, forward_onestep_CPML! = cd_forward_onestep_CPML!, adjoint_onestep_CPML! = cd_adjoint_onestep_CPML!,
                                   prescale_residuals!, correlate_gradient!)
 const Acoustic3D_CD_CPML_B200 = Acoustic2D_CD_CPML_B200          # the C entry points take ndim
+const Acoustic1D_CD_CPML_B200 = Acoustic2D_CD_CPML_B200
 const Acoustic2D_VD_CPML_B200 = (; Data, zeros, ones, forward_onestep_CPML! = vd_forward_onestep_CPML!, adjoint_onestep_CPML! = vd_adjoint_onestep_CPML!,
                                   prescale_residuals!, correlate_gradient_m0!, correlate_gradient_m1!)
+const Acoustic1D_VD_CPML_B200 = Acoustic2D_VD_CPML_B200          # n = (nx, 1)
 const Elastic2D_Iso_CPML_B200 = (; Data, zeros, ones, forward_onestep_CPML! = ela_forward_onestep_CPML!, adjoint_onestep_CPML! = ela_adjoint_onestep_CPML!,
                                   correlate_gradients!)
 
 const FT = Union{Float32, Float64}
+SeismicWaves.select_backend(::CPMLBoundaryCondition, ::LocalGrid, ::Type{<:AcousticCDCPMLWaveSimulation{<:FT, 1}}, ::Type{Val{:B200}}) = Acoustic1D_CD_CPML_B200
+SeismicWaves.select_backend(::CPMLBoundaryCondition, ::LocalGrid, ::Type{<:AcousticVDStaggeredCPMLWaveSimulation{<:FT, 1}}, ::Type{Val{:B200}}) = Acoustic1D_VD_CPML_B200
 SeismicWaves.select_backend(::CPMLBoundaryCondition, ::LocalGrid, ::Type{<:AcousticCDCPMLWaveSimulation{<:FT, 2}}, ::Type{Val{:B200}}) = Acoustic2D_CD_CPML_B200
 SeismicWaves.select_backend(::CPMLBoundaryCondition, ::LocalGrid, ::Type{<:AcousticCDCPMLWaveSimulation{<:FT, 3}}, ::Type{Val{:B200}}) = Acoustic3D_CD_CPML_B200
 SeismicWaves.select_backend(::CPMLBoundaryCondition, ::LocalGrid, ::Type{<:AcousticVDStaggeredCPMLWaveSimulation{<:FT, 2}}, ::Type{Val{:B200}}) = Acoustic2D_VD_CPML_B200

@@ -37,8 +37,8 @@ enum { SWB_OK = 0, SWB_ERR_ARG = 1, SWB_ERR_CUDA = 2, SWB_ERR_STATE = 3, SWB_ERR
 enum { SWB_F32 = 0, SWB_F64 = 1 };
 /* simulation kinds = the reference's concrete WaveSimulation types */
 enum {
-    SWB_ACOU_CD = 1, /* AcousticCDCPMLWaveSimulation{T,N}, N = 2,3   (src/models/acoustic/acou_models.jl:68) */
-    SWB_ACOU_VD = 2, /* AcousticVDStaggeredCPMLWaveSimulation{T,2}  (src/models/acoustic/acou_models.jl:311) */
+    SWB_ACOU_CD = 1, /* AcousticCDCPMLWaveSimulation{T,N}, N = 1,2,3 (src/models/acoustic/acou_models.jl:68) */
+    SWB_ACOU_VD = 2, /* AcousticVDStaggeredCPMLWaveSimulation{T,N}, N = 1,2 (src/models/acoustic/acou_models.jl:311) */
     SWB_ELA_ISO = 3  /* ElasticIsoCPMLWaveSimulation{T,2}           (src/models/elastic/ela_models.jl:177) */
 };
 enum {
@@ -92,9 +92,9 @@ typedef struct {
     int64_t nt;           /* leading dimension of tf */
 } swb_points;
 
-/* Acoustic constant density, N = 2 or 3.
+/* Acoustic constant density, N = 1, 2 or 3.
  * Replaces forward_onestep_CPML! / adjoint_onestep_CPML! of
- * src/models/acoustic/backends/shared/acoustic2D_xPU.jl:78-169 and acoustic3D_xPU.jl:96-219
+ * src/models/acoustic/backends/shared/acoustic1D_xPU.jl:63-125, acoustic2D_xPU.jl:78-169 and acoustic3D_xPU.jl:96-219
  * (kernels update_ψ_*!, update_p_CPML!, inject_sources!, record_receivers!).
  * The caller rotates the field handles afterwards exactly as the reference does (acoustic2D_xPU.jl:121-124);
  * pnew may alias pold. */
@@ -124,10 +124,10 @@ int32_t swb_acou_cd_correlate_gradient(int32_t dtype, int32_t flags, size_t ncel
 int32_t swb_prescale_residuals(int32_t dtype, int32_t ndim, const int64_t *n, void *residuals, int64_t nt, int64_t nrec,
                                const int64_t *posrecs, const void *fact, void *stream);
 
-/* Acoustic variable density (staggered), N = 2.
+/* Acoustic variable density (staggered), N = 2, and N = 1 as the single-row case n = {nx, 1} (the y arrays are then unused and may be NULL).
  * Replaces forward_onestep_CPML! / adjoint_onestep_CPML! of
  * src/models/acoustic/backends/shared/acoustic2D_VD_xPU.jl:91-178 (update_p_CPML!, inject_sources!,
- * update_vx_CPML!, update_vy_CPML!, record_receivers!).  All fields are updated in place. */
+ * update_vx_CPML!, update_vy_CPML!, record_receivers!) and acoustic1D_VD_xPU.jl:77-126.  All fields are updated in place. */
 typedef struct {
     int32_t dtype, halo, flags, _pad;
     int64_t n[2];
@@ -150,7 +150,8 @@ int32_t swb_acou_vd_adjoint_onestep(const swb_acou_vd_step_args *args);  /* v, p
 /* correlate_gradient_m0! -- acoustic/backends/shared/correlate_gradient_xPU.jl:12-21: grad_m0 -= adjp*(p_it - p_itm1)/dt */
 int32_t swb_acou_vd_correlate_gradient_m0(int32_t dtype, int32_t flags, size_t ncells, void *grad_m0, const void *adjp,
                                           const void *p_it, const void *p_itm1, double dt, void *stream);
-/* correlate_gradient_m1! -- acoustic2D_VD_xPU.jl:180-199: grad_m1_d += adjv_d * ∂_d p_it (plain 4-point stencil) */
+/* correlate_gradient_m1! -- acoustic2D_VD_xPU.jl:180-199: grad_m1_d += adjv_d * ∂_d p_it (plain 4-point stencil);
+ * n = {nx, 1}: the 1D method, which runs over (2:nx-2) only (acoustic1D_VD_xPU.jl:127-140) */
 int32_t swb_acou_vd_correlate_gradient_m1(int32_t dtype, int32_t flags, const int64_t *n, const double *spacing, void *const grad_m1_stag[2],
                                           const void *const adjv[2], const void *p_it, void *stream);
 

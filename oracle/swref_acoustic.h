@@ -325,9 +325,11 @@ void FN(acou_vd_correlate_m1)(const FN(acou_vd_geom) * g, REAL *gx, REAL *gy, co
 {
     static const int off4[4] = {-1, 0, 1, 2};
     const long nx = g->n[0], ny = g->n[1];
+    /* the 1D method runs over (2:nx-2) only (acoustic1D_VD_xPU.jl:127-131) */
+    const long ilo = g->ndim == 1 ? 2 : 1, ihi = g->ndim == 1 ? nx - 2 : nx - 1;
 #pragma omp parallel for schedule(static)
     for (long j = 1; j <= ny; ++j)
-        for (long i = 1; i <= nx - 1; ++i) {
+        for (long i = ilo; i <= ihi; ++i) {
             double D = FN(fd_bd)(p + (size_t)(j - 1) * (size_t)nx, 1, nx, i, g->c_d1o4, off4, 4, g->inv_d[0]);
             size_t q = (size_t)(j - 1) * (size_t)(nx - 1) + (size_t)(i - 1);
             gx[q] = (REAL)(gx[q] + adjvx[q] * D);

@@ -328,8 +328,8 @@ class AcousticVDStaggeredCPMLWaveSimulation(_AcousticBase):
         self._bind_scalar(shot, tf, possrcs, posrecs)
 
     def _snapshot_fields(self):
-        nx, ny = self.gridsize
-        return {"pcur": [self.gridsize], "vcur": [(nx - 1, ny), (nx, ny - 1)]}
+        n = self.gridsize
+        return {"pcur": [n], "vcur": [tuple(n[j] - (1 if i == j else 0) for j in range(self.N)) for i in range(self.N)]}
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -99,10 +99,10 @@ template <class T, class CT, int NDIM>
 __global__ void __launch_bounds__(256) cd_update_p_kernel(CdParams<T> P)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1; // 0-based, interior starts at 1
-    const long long j = (long long)blockIdx.y * blockDim.y + threadIdx.y + 1;
+    const long long j = NDIM >= 2 ? (long long)blockIdx.y * blockDim.y + threadIdx.y + 1 : 0;
     const long long k = NDIM == 3 ? (long long)blockIdx.z + 1 : 0;
     const long long nx = P.n[0], ny = P.n[1];
-    if (i > nx - 2 || j > ny - 2)
+    if (i > nx - 2 || (NDIM >= 2 && j > ny - 2))
         return;
     const size_t q = lin3(i, j, k, nx, ny);
     const T *pc = P.pcur + q;
@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(256) cd_update_p_kernel(CdParams<T> P)
     CT lap = cd_d2_axis<T, CT>(P, 0, pc, 1, i + 1, P.psi[0] + (size_t)(2 * h) * ((size_t)k * ny + j), 1,
                                P.xi[0] + (size_t)(2 * (h + 1)) * ((size_t)k * ny + j), 1);
     // psi_y (nx, 2h, nz), xi_y (nx, 2(h+1), nz)
-    lap = lap + cd_d2_axis<T, CT>(P, 1, pc, nx, j + 1, P.psi[1] + (size_t)k * nx * (2 * h) + i, nx,
-                                  P.xi[1] + (size_t)k * nx * (2 * (h + 1)) + i, nx);
+    if (NDIM >= 2)
+        lap = lap + cd_d2_axis<T, CT>(P, 1, pc, nx, j + 1, P.psi[1] + (size_t)k * nx * (2 * h) + i, nx,
+                                      P.xi[1] + (size_t)k * nx * (2 * (h + 1)) + i, nx);
     if (NDIM == 3) // psi_z (nx, ny, 2h), xi_z (nx, ny, 2(h+1))
         lap = lap + cd_d2_axis<T, CT>(P, 2, pc, nx * ny, k + 1, P.psi[2] + (size_t)j * nx + i, nx * ny,
                                       P.xi[2] + (size_t)j * nx + i, nx * ny);
@@ -184,7 +185,7 @@ template <class T>
 static CdParams<T> make_params(const swb_acou_cd_step_args &a)
 {
     CdParams<T> P{};
-    SWB_REQUIRE(a.ndim == 2 || a.ndim == 3, "acoustic CD: ndim must be 2 or 3");
+    SWB_REQUIRE(a.ndim >= 1 && a.ndim <= 3, "acoustic CD: ndim must be 1, 2 or 3");
     SWB_REQUIRE(a.halo >= 0, "CPML halo size must be non-negative!");
     P.ndim = a.ndim;
     P.halo = a.halo;
@@ -261,7 +262,9 @@ static void cd_step_impl(const swb_acou_cd_step_args &a, bool record)
         count_launch();
     }
     dim3 blk(32, 8, 1);
-    if (a.ndim == 2) {
+    if (a.ndim == 1) { // acoustic1D_xPU.jl:78-95
+        cd_update_p_kernel<T, CT, 1><<<cdiv(P.n[0] - 2, 256), 256, 0, st>>>(P);
+    } else if (a.ndim == 2) {
         dim3 grd(cdiv(P.n[0] - 2, 32), cdiv(P.n[1] - 2, 8), 1);
         cd_update_p_kernel<T, CT, 2><<<grd, blk, 0, st>>>(P);
     } else {

@@ -1,4 +1,7 @@
-// acou_vd.cu -- 2D acoustic variable-density staggered pressure/velocity update with C-PML.
+// acou_vd.cu -- 2D (and 1D) acoustic variable-density staggered pressure/velocity update with C-PML.
+//
+// A 1D grid (acoustic1D_VD_xPU.jl:1-140) is the ny = 1 case of the same kernels: no y derivative, no vy, the pressure update runs
+// over (2:nx-1) of the single row and correlate_gradient_m1! over (2:nx-2) (acoustic1D_VD_xPU.jl:127-131).
 //
 // Reference semantics: src/models/acoustic/backends/shared/acoustic2D_VD_xPU.jl:1-199,
 // src/models/acoustic/backends/shared/correlate_gradient_xPU.jl:12-21, stencils from
@@ -53,11 +56,12 @@ __device__ __forceinline__ CT fd4_bd(const T *A, long long stride, long long n, 
 template <class T, class CT>
 __global__ void __launch_bounds__(256) vd_update_p_kernel(VdParams<T> P)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + 2; // 1-based
-    const long long j = (long long)blockIdx.y * blockDim.y + threadIdx.y + 2;
     const long long nx = P.nx, ny = P.ny;
+    const bool one_d = ny == 1;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + 2; // 1-based
+    const long long j = one_d ? 1 : (long long)blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int h = P.halo;
-    if (i > nx - 1 || j > ny - 1)
+    if (i > nx - 1 || (one_d ? threadIdx.y != 0 || blockIdx.y != 0 : j > ny - 1))
         return;
     // dvx/dx: array vx (nx-1, ny), I = i-1, halfgrid=false -> idim = i, ndim = nx
     CT Dx = fd4_bd<T, CT>(P.vx + (size_t)(j - 1) * (nx - 1), 1, nx - 1, i - 1, P.c4, P.inv_dx);
@@ -68,6 +72,11 @@ __global__ void __launch_bounds__(256) vd_update_p_kernel(VdParams<T> P)
         Dx = cpml_apply<T, CT>(Dx, P.a_x[ii - 1], P.b_x[ii - 1], *x, xn);
         *x = xn;
     }
+    const size_t q = (size_t)(j - 1) * nx + (i - 1);
+    if (one_d) { // acoustic1D_VD_xPU.jl:28: pcur[i] -= fact_m0[i] * ∂vx∂x
+        P.p[q] = (T)((CT)P.p[q] - (CT)P.m0[q] * Dx);
+        return;
+    }
     CT Dy = fd4_bd<T, CT>(P.vy + (i - 1), nx, ny - 1, j - 1, P.c4, P.inv_dy);
     if (j <= h + 1 || j >= ny - h) {
         long long jj = j <= h + 1 ? j : j - ny + 2 * h + 2;
@@ -76,7 +85,6 @@ __global__ void __launch_bounds__(256) vd_update_p_kernel(VdParams<T> P)
         Dy = cpml_apply<T, CT>(Dy, P.a_y[jj - 1], P.b_y[jj - 1], *x, xn);
         *x = xn;
     }
-    const size_t q = (size_t)(j - 1) * nx + (i - 1);
     P.p[q] = (T)((CT)P.p[q] - (CT)P.m0[q] * (Dx + Dy));
 }
 
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(256) vd_correlate_m1_kernel(T *gx, T *gy, cons
     if (i > nx || j > ny)
         return;
     const double c[4] = {c0, c1, c2, c3};
-    if (i <= nx - 1) {
+    if (ny == 1 ? (i >= 2 && i <= nx - 2) : i <= nx - 1) { // 1D: (2:nx-2), acoustic1D_VD_xPU.jl:130
         CT D = fd4_bd<T, CT>(p + (size_t)(j - 1) * nx, 1, nx, i, c, inv_dx);
         const size_t q = (size_t)(j - 1) * (nx - 1) + (i - 1);
         gx[q] = (T)((CT)gx[q] + (CT)avx[q] * D);
@@ -156,13 +164,13 @@ static VdParams<T> make_params(const swb_acou_vd_step_args &a)
 {
     VdParams<T> P{};
     SWB_REQUIRE(a.halo >= 0, "CPML halo size must be non-negative!");
-    for (int d = 0; d < 2; ++d)
-        SWB_REQUIRE(a.n[d] >= 2 * (int64_t)a.halo + 3, "Number grid points in the dimensions with C-PML boundaries must be at least 2*halo+3!");
+    for (int d = 0; d < 2; ++d) // n[1] = 1: a 1D grid
+        SWB_REQUIRE(a.n[d] >= 2 * (int64_t)a.halo + 3 || (d == 1 && a.n[1] == 1), "Number grid points in the dimensions with C-PML boundaries must be at least 2*halo+3!");
     P.halo = a.halo;
     P.nx = a.n[0];
     P.ny = a.n[1];
     P.inv_dx = (T)1 / (T)a.spacing[0];
-    P.inv_dy = (T)1 / (T)a.spacing[1];
+    P.inv_dy = a.n[1] == 1 ? (T)0 : (T)1 / (T)a.spacing[1];
     P.p = (T *)a.pcur;
     P.vx = (T *)a.vcur[0];
     P.vy = (T *)a.vcur[1];
@@ -190,7 +198,9 @@ static VdParams<T> make_params(const swb_acou_vd_step_args &a)
 template <class T, class CT>
 static void launch_p(const VdParams<T> &P, cudaStream_t st)
 {
-    dim3 blk(32, 8, 1), grd(cdiv(P.nx - 2, 32), cdiv(P.ny - 2, 8), 1);
+    dim3 blk(32, 8, 1), grd(cdiv(P.nx - 2, 32), P.ny == 1 ? 1 : cdiv(P.ny - 2, 8), 1);
+    if (P.ny == 1)
+        blk = dim3(256, 1, 1), grd = dim3(cdiv(P.nx - 2, 256), 1, 1);
     vd_update_p_kernel<T, CT><<<grd, blk, 0, st>>>(P);
     check_launch("vd_update_p");
     count_launch();
@@ -211,14 +221,16 @@ static void vd_step_impl(const swb_acou_vd_step_args &a, bool adjoint)
     VdParams<T> P = make_params<T>(a);
     cudaStream_t st = (cudaStream_t)a.stream;
     if (!adjoint) { // p, inject, v, record (acoustic2D_VD_xPU.jl:117-137)
+        const int nd = a.n[1] == 1 ? 1 : 2; // positions are (npos, ndim)
         launch_p<T, CT>(P, st);
-        launch_inject<T>(P.p, 2, a.n, a.src, a.it, st);
+        launch_inject<T>(P.p, nd, a.n, a.src, a.it, st);
         launch_v<T, CT>(P, st);
-        launch_record<T>(P.p, 2, a.n, a.rec, a.it, st);
+        launch_record<T>(P.p, nd, a.n, a.rec, a.it, st);
     } else { // v, p, inject (acoustic2D_VD_xPU.jl:163-178)
+        const int nd = a.n[1] == 1 ? 1 : 2;
         launch_v<T, CT>(P, st);
         launch_p<T, CT>(P, st);
-        launch_inject<T>(P.p, 2, a.n, a.src, a.it, st);
+        launch_inject<T>(P.p, nd, a.n, a.src, a.it, st);
     }
 }
 

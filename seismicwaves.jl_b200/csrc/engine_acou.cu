@@ -21,7 +21,7 @@ class AcousticCD : public SimBase {
     // own_state = false: a subclass keeps the wavefield state in its own layout (fused engine below)
     explicit AcousticCD(const swb_sim_desc &d, bool own_state = true) : SimBase(d)
     {
-        SWB_REQUIRE(d.ndim == 2 || d.ndim == 3, "acoustic constant-density engine supports N = 2, 3");
+        SWB_REQUIRE(d.ndim >= 1 && d.ndim <= 3, "acoustic constant-density engine supports N = 1, 2, 3");
         const size_t nb = ncells() * esize;
         fact_ = dalloc(nb);
         vp_ = dalloc(nb);
@@ -333,7 +333,8 @@ class AcousticCD : public SimBase {
 SimBase *make_acoustic_cd(const swb_sim_desc &d)
 {
     // the fused single-launch engine is the default; SWB_FLAG_NO_FUSION selects the one-launch-per-reference-kernel path
-    if (!(d.flags & SWB_FLAG_NO_FUSION))
+    // (1D grids, acoustic1D_xPU.jl, are a few thousand cells: the per-kernel path is all they need)
+    if (!(d.flags & SWB_FLAG_NO_FUSION) && d.ndim >= 2)
         return new AcousticCDFused(d);
     return new AcousticCD(d);
 }
@@ -346,9 +347,11 @@ class AcousticVD : public SimBase {
     // own_state = false: a subclass keeps the wavefield state in its own layout (fused engine below)
     explicit AcousticVD(const swb_sim_desc &d, bool own_state = true) : SimBase(d)
     {
-        SWB_REQUIRE(d.ndim == 2, "acoustic variable-density engine supports N = 2");
+        SWB_REQUIRE(d.ndim == 1 || d.ndim == 2, "acoustic variable-density engine supports N = 1, 2");
         nx_ = d.n[0];
-        ny_ = d.n[1];
+        ny_ = d.ndim == 1 ? 1 : d.n[1]; // a 1D grid is the single-row case of the same kernels (acou_vd.cu)
+        nn_[0] = nx_, nn_[1] = ny_;
+        nd_ = d.ndim;
         const size_t nb = ncells() * esize, nbx = (size_t)(nx_ - 1) * ny_ * esize, nby = (size_t)nx_ * (ny_ - 1) * esize;
         const size_t h = (size_t)d.halo;
         vp_ = dalloc(nb);
@@ -408,7 +411,7 @@ class AcousticVD : public SimBase {
             upload(rho_.p, fields[1], rho_.bytes);
         }
         interp_ = interp;
-        post_vd_facts(desc.dtype, desc.n, vp_.p, rho_.p, desc.dt, interp, m0_.p, m1_[0].p, m1_[1].p, stream);
+        post_vd_facts(desc.dtype, nn_, vp_.p, rho_.p, desc.dt, interp, m0_.p, m1_[0].p, m1_[1].p, stream);
         mat_set_ = true;
     }
 
@@ -460,19 +463,19 @@ class AcousticVD : public SimBase {
         SWB_REQUIRE(desc.gradient, "simulation was not built with gradient=true");
         // acou_gradient.jl:177-202
         d2d(work_.p, g0_.p, g0_.bytes);
-        post_vd_backinterp(desc.dtype, desc.n, rho_.p, interp_, g1s_[0].p, g1s_[1].p, g1_.p, stream);
+        post_vd_backinterp(desc.dtype, nn_, rho_.p, interp_, g1s_[0].p, g1s_[1].p, g1_.p, stream);
         DevBuf &sp = mute_pos_[0], &rp = mute_pos_[1]; // persistent scratch (no cudaMalloc / cudaFree inside the shot loop)
         if (rs != 0 && nsrcpos > 0) {
-            ensure(sp, esize * nsrcpos * 2);
+            ensure(sp, esize * nsrcpos * nd_);
             upload(sp.p, srcpos, sp.bytes);
-            post_mute(desc.dtype, 2, desc.n, desc.spacing, work_.p, nsrcpos, sp.p, rs, stream);
-            post_mute(desc.dtype, 2, desc.n, desc.spacing, g1_.p, nsrcpos, sp.p, rs, stream);
+            post_mute(desc.dtype, nd_, nn_, desc.spacing, work_.p, nsrcpos, sp.p, rs, stream);
+            post_mute(desc.dtype, nd_, nn_, desc.spacing, g1_.p, nsrcpos, sp.p, rs, stream);
         }
         if (rr != 0 && nrecpos > 0) {
-            ensure(rp, esize * nrecpos * 2);
+            ensure(rp, esize * nrecpos * nd_);
             upload(rp.p, recpos, rp.bytes);
-            post_mute(desc.dtype, 2, desc.n, desc.spacing, work_.p, nrecpos, rp.p, rr, stream);
-            post_mute(desc.dtype, 2, desc.n, desc.spacing, g1_.p, nrecpos, rp.p, rr, stream);
+            post_mute(desc.dtype, nd_, nn_, desc.spacing, work_.p, nrecpos, rp.p, rr, stream);
+            post_mute(desc.dtype, nd_, nn_, desc.spacing, g1_.p, nrecpos, rp.p, rr, stream);
         }
         post_vd_chain_accumulate(desc.dtype, ncells(), work_.p, g1_.p, vp_.p, rho_.p, total_grad_[0].p, total_grad_[1].p, stream);
         sync();
@@ -510,7 +513,7 @@ class AcousticVD : public SimBase {
         use_device();
         SWB_REQUIRE(mat_set_, "material properties not set");
         SWB_REQUIRE(shot_bound_, "no shot bound");
-        SWB_REQUIRE(cpml_set_[0] && cpml_set_[1], "C-PML coefficients not set for every axis");
+        SWB_REQUIRE(cpml_set_[0] && (nd_ == 1 || cpml_set_[1]), "C-PML coefficients not set for every axis");
         zero(p_);
         for (int k = 0; k < 2; ++k) {
             zero(v_[k]);
@@ -539,7 +542,7 @@ class AcousticVD : public SimBase {
         a.halo = desc.halo;
         a.flags = desc.flags;
         for (int k = 0; k < 2; ++k) {
-            a.n[k] = desc.n[k];
+            a.n[k] = nn_[k];
             a.spacing[k] = desc.spacing[k];
             a.cpml[k] = cpml_axis(k);
             a.fact_m1_stag[k] = m1_[k].p;
@@ -606,7 +609,7 @@ class AcousticVD : public SimBase {
     // acou_gradient.jl:141-176
     virtual void adjoint_loop()
     {
-        prescale_residuals(desc.dtype, 2, desc.n, adjsrc_.p, desc.nt, nrec_, posrec_.as<int64_t>(), m0_.p, stream);
+        prescale_residuals(desc.dtype, nd_, nn_, adjsrc_.p, desc.nt, nrec_, posrec_.as<int64_t>(), m0_.p, stream);
         for (int64_t it = desc.nt; it >= 1; --it) {
             step_adjoint(it);
             if (!ckpt_->is_saved(0, it - 1)) {
@@ -629,7 +632,7 @@ class AcousticVD : public SimBase {
             vd_correlate_m0(desc.dtype, ncells(), g0_.p, ap_.p, p_it, p_itm1, desc.dt, stream);
             void *g[2] = {g1s_[0].p, g1s_[1].p};
             const void *av[2] = {av_[0].p, av_[1].p};
-            vd_correlate_m1(desc.dtype, desc.flags, desc.n, desc.spacing, g, av, p_it, stream);
+            vd_correlate_m1(desc.dtype, desc.flags, nn_, desc.spacing, g, av, p_it, stream);
         }
         sync();
     }
@@ -645,7 +648,8 @@ class AcousticVD : public SimBase {
         snapshots_[it] = std::move(comps);
     }
 
-    int64_t nx_, ny_;
+    int64_t nx_, ny_, nn_[2] = {0, 0};
+    int nd_ = 2;
     int interp_ = 0;
     DevBuf vp_, rho_, m0_, m1_[2], p_, v_[2], psi_[2], xi_[2];
     DevBuf g0_, g1s_[2], g1_, work_, ap_, av_[2], psi_adj_[2], xi_adj_[2], misfit_acc_, obs_, mute_pos_[2];
@@ -659,7 +663,7 @@ SimBase *make_acoustic_vd(const swb_sim_desc &d)
 {
     // the fused single-launch engine is the default; SWB_FLAG_NO_FUSION (or a grid smaller than one stencil)
     // selects the one-launch-per-reference-kernel path
-    if (!(d.flags & SWB_FLAG_NO_FUSION) && d.n[0] >= 8 && d.n[1] >= 8)
+    if (!(d.flags & SWB_FLAG_NO_FUSION) && d.ndim == 2 && d.n[0] >= 8 && d.n[1] >= 8)
         return new AcousticVDFused(d);
     return new AcousticVD(d);
 }

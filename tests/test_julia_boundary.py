@@ -246,7 +246,8 @@ def test_backend_tuples_expose_the_members_the_reference_calls(jl_src):
         have = {p.split("=")[0].strip() for p in split_top(m.group(1))}
         assert members <= have, (name, members - have)
     assert "const Acoustic3D_CD_CPML_B200 = Acoustic2D_CD_CPML_B200" in jl_src
-    for kind, n in (("AcousticCDCPMLWaveSimulation", 2), ("AcousticCDCPMLWaveSimulation", 3), ("AcousticVDStaggeredCPMLWaveSimulation", 2), ("ElasticIsoCPMLWaveSimulation", 2)):
+    for kind, n in (("AcousticCDCPMLWaveSimulation", 1), ("AcousticCDCPMLWaveSimulation", 2), ("AcousticCDCPMLWaveSimulation", 3),
+                    ("AcousticVDStaggeredCPMLWaveSimulation", 1), ("AcousticVDStaggeredCPMLWaveSimulation", 2), ("ElasticIsoCPMLWaveSimulation", 2)):
         assert re.search(rf"SeismicWaves\.select_backend\(::CPMLBoundaryCondition, ::LocalGrid, ::Type\{{<:{kind}\{{<:FT, {n}\}}\}}, ::Type\{{Val\{{:B200\}}\}}\)", jl_src), (kind, n)
     # the two elastic forward methods differ by the three moment-tensor arguments, as at ela_forward.jl:53-69,127-144
     sigs = re.findall(r"function ela_forward_onestep_CPML!\((.*?)\)\n", jl_src, flags=re.S)
