@@ -197,6 +197,11 @@ end
 struct L2Spec                  # swb_l2_spec
     observed::Ptr{Cvoid}; invcov_diag::Ptr{Cvoid}; mask::Ptr{Cvoid}
 end
+struct SlabHandle              # swb_slab_handle
+    ipc::NTuple{192, UInt8}; raw::NTuple{3, UInt64}
+    nz::Int64; plane_elems::Int64
+    device::Int32; pid::Int32
+end
 
 pad3(t::NTuple{N, T}, z) where {N, T} = ntuple(i -> i <= N ? t[i] : z, 3)
 pad2(t::NTuple{N, T}, z) where {N, T} = ntuple(i -> i <= N ? t[i] : z, 2)
@@ -714,6 +719,28 @@ end
 function set_slab!(model::AcousticCDCPMLWaveSimulation{T, 3, <:B200Array}, comm::Ptr{Cvoid}, lower::Integer, upper::Integer) where {T}
     check(ccall((:swb_sim_set_slab, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32), engine(model), comm, Int32(lower), Int32(upper)))
     return model
+end
+
+# The same decomposition with the halo exchange through peer memory (no communicator): `slabs[k]` is the slab-local simulation of
+# slab k, bottom to top, each on its own GPU (set_device!).  After this call the step kernels store the boundary planes straight into
+# the neighbours' ghost planes over NVLink and per-step flags keep the slabs in lockstep; run every slab's swforward_1shot! from its
+# own task (Threads.@spawn): a slab's call blocks until its neighbours have caught up.
+function connect_slabs!(slabs::Vector{<:AcousticCDCPMLWaveSimulation{T, 3, <:B200Array}}) where {T}
+    n = length(slabs)
+    for (k, m) in enumerate(slabs)
+        set_slab!(m, C_NULL, k > 1 ? k - 2 : -1, k < n ? k : -1)
+    end
+    handles = map(slabs) do m
+        h = Ref{SlabHandle}()
+        check(ccall((:swb_sim_slab_export, lib), Int32, (Ptr{Cvoid}, Ref{SlabHandle}), engine(m), h))
+        h
+    end
+    for (k, m) in enumerate(slabs)
+        lo = k > 1 ? Base.unsafe_convert(Ptr{SlabHandle}, handles[k - 1]) : Ptr{SlabHandle}(C_NULL)
+        hi = k < n ? Base.unsafe_convert(Ptr{SlabHandle}, handles[k + 1]) : Ptr{SlabHandle}(C_NULL)
+        GC.@preserve handles check(ccall((:swb_sim_slab_connect, lib), Int32, (Ptr{Cvoid}, Ptr{SlabHandle}, Ptr{SlabHandle}), engine(m), lo, hi))
+    end
+    return slabs
 end
 
 end # module

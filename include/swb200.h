@@ -342,6 +342,25 @@ int32_t swb_sim_allreduce_total_gradient(swb_sim *sim, swb_comm *comm);
  * with NCCL point-to-point transfers on the sim's stream.  Call before swb_sim_bind_scalar_shot; positions are slab-local. */
 int32_t swb_sim_set_slab(swb_sim *sim, swb_comm *comm, int32_t lower_rank, int32_t upper_rank);
 
+/* Halo exchange through peer memory instead of NCCL (NVLink / NVSwitch peer stores fused into the step kernels): after swb_sim_set_slab every
+ * slab exports a handle of its two rotating pressure planes and of its flag word, the caller passes the handles around (Julia: same
+ * process; Python: one all-gather of 256 bytes per rank), and every slab connects to its neighbours' handles.  From then on the kernels
+ * that compute the first / last owned plane also store it into the neighbour's ghost plane, and neighbouring slabs are kept within one
+ * time step of each other by stream-ordered 32-bit flag writes / waits (cuStreamWriteValue32 / cuStreamWaitValue32) in each other's
+ * memory: no collective, no host synchronisation, no extra pass over the planes.  Handles from the same process are used as plain
+ * pointers (peer access is enabled between devices), handles from another process are opened with cudaIpcOpenMemHandle.  Every slab of a
+ * decomposition must run the same sequence of shots; a slab driven from one host thread per sim (its forward call blocks until its
+ * neighbours have caught up).  comm may be NULL in swb_sim_set_slab when this exchange is used. */
+typedef struct {
+    uint8_t ipc[192];         /* three cudaIpcMemHandle_t (64 bytes each): rotating plane 0, rotating plane 1, flag buffer */
+    uint64_t raw[3];          /* the same three device pointers, valid inside the exporting process */
+    int64_t nz;               /* planes of the exporting slab (ghost planes included) */
+    int64_t plane_elems;      /* elements per plane (row pitch x ny) */
+    int32_t device, pid;
+} swb_slab_handle;
+int32_t swb_sim_slab_export(swb_sim *sim, swb_slab_handle *handle_out);
+int32_t swb_sim_slab_connect(swb_sim *sim, const swb_slab_handle *lower_or_null, const swb_slab_handle *upper_or_null);
+
 #ifdef __cplusplus
 }
 #endif

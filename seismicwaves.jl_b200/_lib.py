@@ -105,6 +105,10 @@ class swb_l2_spec(C.Structure):
     _fields_ = [("observed", C.c_void_p), ("invcov_diag", C.c_void_p), ("mask", C.c_void_p)]
 
 
+class swb_slab_handle(C.Structure):
+    _fields_ = [("ipc", C.c_uint8 * 192), ("raw", C.c_uint64 * 3), ("nz", C.c_int64), ("plane_elems", C.c_int64), ("device", C.c_int32), ("pid", C.c_int32)]
+
+
 # every symbol include/swb200.h declares (tests check the header against this list and the .so against both)
 EXPORTS = [
     "swb_last_error", "swb_abi_version", "swb_abi_layout", "swb_device_count", "swb_launch_count",
@@ -118,6 +122,7 @@ EXPORTS = [
     "swb_sim_accumulate_gradient", "swb_sim_zero_total_gradient", "swb_sim_total_gradient_ptr", "swb_sim_get_total_gradient",
     "swb_sim_cell_updates", "swb_sim_get_field", "swb_sim_stream", "swb_sim_kernel_timing", "swb_sim_kernel_timing_class",
     "swb_comm_unique_id", "swb_comm_create", "swb_comm_destroy", "swb_comm_allreduce_sum", "swb_sim_allreduce_total_gradient", "swb_sim_set_slab",
+    "swb_sim_slab_export", "swb_sim_slab_connect",
 ]
 
 _lib = None
@@ -192,6 +197,8 @@ def load() -> C.CDLL:
         "swb_comm_allreduce_sum": [vp, vp, sz, i32, vp],
         "swb_sim_allreduce_total_gradient": [vp, vp],
         "swb_sim_set_slab": [vp, vp, i32, i32],
+        "swb_sim_slab_export": [vp, C.POINTER(swb_slab_handle)],
+        "swb_sim_slab_connect": [vp, C.POINTER(swb_slab_handle), C.POINTER(swb_slab_handle)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)

@@ -224,6 +224,10 @@ __device__ __forceinline__ void cd_bulk_body(const CdFusedParams<T> &P, const in
             if (has_inj)
                 inject_points<T, V>(P, P.inj[0], cta, code0, out);
             stv<T, V>(P.pnew + off, out);
+            if (P.peer_lo != nullptr && k == 1) // boundary planes of a z slab go straight into the neighbour's ghost plane (NVLink peer store)
+                stv<T, V>(P.peer_lo + (off - plane), out);
+            if (P.peer_hi != nullptr && k == P.nz - 2)
+                stv<T, V>(P.peer_hi + (off - (long long)(P.nz - 2) * plane), out);
             if (has_rec)
                 record_points<T, V>(P, P.rec[0], cta, code0, out);
             if (ADJ) {
@@ -363,6 +367,8 @@ __device__ __forceinline__ void cd_rim_body(const CdFusedParams<T> &P, const int
     const int j = B.j0 + (int)(r - kk * (unsigned)B.ny), k = B.k0 + (int)kk;
     const int i0 = iv * V;
     const int nx = P.nx, ny = P.ny, nz = P.nz, h = P.halo;
+    if ((k == 0 && P.ghost_lo) || (k == nz - 1 && P.ghost_hi))
+        return; // a ghost plane of a z slab: written by the neighbour that owns it
     const long long ld = P.ld, plane = P.plane;
     const long long off = (long long)k * plane + (long long)j * ld + i0;
 
@@ -441,6 +447,10 @@ __device__ __forceinline__ void cd_rim_body(const CdFusedParams<T> &P, const int
     if (P.inj_it > 0)
         inject_points<T, V>(P, P.inj[1], cta, code0, out);
     stv<T, V>(P.pnew + off, out);
+    if (P.peer_lo != nullptr && k == 1)
+        stv<T, V>(P.peer_lo + (off - plane), out);
+    if (P.peer_hi != nullptr && k == nz - 2)
+        stv<T, V>(P.peer_hi + (off - (long long)(nz - 2) * plane), out);
     if (P.rec_it > 0)
         record_points<T, V>(P, P.rec[1], cta, code0, out);
     if (ADJ) {

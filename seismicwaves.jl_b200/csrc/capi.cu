@@ -258,6 +258,7 @@ std::string build_layout()
     SWB_L_F(check_freq) SWB_L_F(flags) SWB_L_F(_pad) SWB_L_END
     SWB_L_BEGIN(swb_sinc_points_host) SWB_L_F(n) SWB_L_F(off) SWB_L_F(ij) SWB_L_F(coef) SWB_L_END
     SWB_L_BEGIN(swb_l2_spec) SWB_L_F(observed) SWB_L_F(invcov_diag) SWB_L_F(mask) SWB_L_END
+    SWB_L_BEGIN(swb_slab_handle) SWB_L_F(ipc) SWB_L_F(raw) SWB_L_F(nz) SWB_L_F(plane_elems) SWB_L_F(device) SWB_L_F(pid) SWB_L_END
     w.s += "}";
     return w.s;
 }
@@ -518,11 +519,20 @@ int32_t swb_sim_allreduce_total_gradient(swb_sim *sim, swb_comm *comm)
     SWB_API_END
 }
 
+int32_t swb_sim_slab_export(swb_sim *sim, swb_slab_handle *handle_out)
+{
+    SIM_CALL(SWB_REQUIRE(handle_out != nullptr, "null handle"); sim->impl->slab_export(handle_out))
+}
+
+int32_t swb_sim_slab_connect(swb_sim *sim, const swb_slab_handle *lower_or_null, const swb_slab_handle *upper_or_null)
+{
+    SIM_CALL(sim->impl->slab_connect(lower_or_null, upper_or_null))
+}
+
 int32_t swb_sim_set_slab(swb_sim *sim, swb_comm *comm, int32_t lower_rank, int32_t upper_rank)
 {
     SWB_API_BEGIN
     SWB_REQUIRE(sim != nullptr && sim->impl, "null simulation handle");
-    SWB_REQUIRE(comm != nullptr || (lower_rank < 0 && upper_rank < 0), "a communicator is required when the slab has neighbours");
     if (comm) {
         SWB_REQUIRE(lower_rank < comm->nranks && upper_rank < comm->nranks && lower_rank != comm->rank && upper_rank != comm->rank, "bad neighbour rank");
         SWB_REQUIRE(comm->device == sim->impl->desc.device, "communicator and simulation live on different devices");

@@ -35,6 +35,12 @@ template <class T>
 struct CdFusedParams {
     int nx, ny, nz, halo;
     int zpml_lo, zpml_hi;  // 0: that z end is an interior face of a z-slab decomposition (one ghost plane, no C-PML strip)
+    // z-slab decomposition with the halo exchange fused into the step (peer memory over NVLink): the freshly computed first / last
+    // owned plane (k = 1 / k = nz - 2) is also stored into the neighbour's ghost plane -- peer_lo / peer_hi point at that plane of
+    // the neighbour's pnew (null: no neighbour, or the exchange is done by NCCL after the step).  ghost_lo / ghost_hi: plane 0 /
+    // nz - 1 is a ghost plane the neighbour owns; this slab's kernels leave it alone.
+    T *peer_lo, *peer_hi;
+    int ghost_lo, ghost_hi;
     long long ld, plane;   // row pitch and plane pitch (elements) of pcur / pold / pnew / fact / grad / stored fields
     T inv_d[3];            // 1 / spacing along kernel axes x, y, z
     const T *pcur, *pold, *fact;

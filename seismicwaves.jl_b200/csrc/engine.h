@@ -125,6 +125,9 @@ class SimBase {
     // the adjoint loop of swgradient_1shot! on the adjoint source in adjsrc_ (after gradient_forward)
     virtual void adjoint_loop() = 0;
     virtual void set_slab(swb_comm *, int, int) { throw Error(SWB_ERR_ARG, "z-slab decomposition is available for the fused 3D acoustic constant-density engine only"); }
+    // peer-memory halo exchange of a z-slab decomposition (include/swb200.h, swb_slab_handle)
+    virtual void slab_export(swb_slab_handle *) { throw Error(SWB_ERR_ARG, "z-slab decomposition is available for the fused 3D acoustic constant-density engine only"); }
+    virtual void slab_connect(const swb_slab_handle *, const swb_slab_handle *) { throw Error(SWB_ERR_ARG, "z-slab decomposition is available for the fused 3D acoustic constant-density engine only"); }
     void zero_total_gradient();
     void total_gradient_ptr(int which, void **p, size_t *nelem);
     void get_total_gradient(int which, void *host_out);
@@ -249,6 +252,12 @@ void SimBase::run_graph(Graph &g, F &&enqueue)
     cell_updates += g.updates;
     g_launches.fetch_add(g.launches);
 }
+
+// stream-ordered 32-bit flag operations (cuStreamWriteValue32 / cuStreamWaitValue32 resolved through cudaGetDriverEntryPoint; engine_core.cu):
+// the write is preceded by a system-wide memory barrier, so everything enqueued on the stream before it -- peer stores over NVLink
+// included -- is visible to whoever observes the value; the wait blocks the stream until *addr >= value (wrap-around compare)
+void stream_write_flag(cudaStream_t st, void *dev_addr, uint32_t value);
+void stream_wait_flag_geq(cudaStream_t st, void *dev_addr, uint32_t value);
 
 // capi.cu (NCCL is resolved there)
 void comm_halo_exchange(swb_comm *comm, const void *send_lo, void *recv_lo, int lower, const void *send_hi, void *recv_hi, int upper, size_t nelem, int dtype,

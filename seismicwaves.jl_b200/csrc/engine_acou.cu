@@ -10,6 +10,7 @@
 #include "cd_fused.h"
 #include "tma.cuh"
 #include <cstring>
+#include <unistd.h>
 
 namespace swb {
 

@@ -1,6 +1,7 @@
 // engine_core.cu -- device memory, checkpoint storage and the parts of the per-shot engine that do not
 // depend on the physics.
 #include "engine.h"
+#include <cuda.h>
 #include <algorithm>
 #include <cstring>
 #include <cmath>
@@ -31,6 +32,35 @@ void make_tmap_2d(CUtensorMap *out, int dtype, const void *base, long long ld, l
         throw Error(SWB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
 }
 
+
+namespace {
+typedef CUresult (*memop32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+memop32_fn driver_memop(const char *name)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SWB_CUDA(cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
+        throw Error(SWB_ERR_CUDA, std::string(name) + " is not available in this driver");
+    return (memop32_fn)fn;
+}
+} // namespace
+
+void stream_write_flag(cudaStream_t st, void *dev_addr, uint32_t value)
+{
+    static memop32_fn fn = driver_memop("cuStreamWriteValue32");
+    const CUresult r = fn((CUstream)st, (CUdeviceptr)dev_addr, value, CU_STREAM_WRITE_VALUE_DEFAULT);
+    if (r != CUDA_SUCCESS)
+        throw Error(SWB_ERR_CUDA, "cuStreamWriteValue32 failed with CUresult " + std::to_string((int)r));
+}
+
+void stream_wait_flag_geq(cudaStream_t st, void *dev_addr, uint32_t value)
+{
+    static memop32_fn fn = driver_memop("cuStreamWaitValue32");
+    const CUresult r = fn((CUstream)st, (CUdeviceptr)dev_addr, value, CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS)
+        throw Error(SWB_ERR_CUDA, "cuStreamWaitValue32 failed with CUresult " + std::to_string((int)r));
+}
 
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_device_bytes{0};

@@ -61,6 +61,19 @@ class ShotParallel:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allgather_bytes(self, payload: bytes) -> list:
+        """every rank's `payload` (equal lengths), in rank order"""
+        import torch
+
+        if self.world == 1:
+            return [payload]
+        on_gpu = self.dist.get_backend() == "nccl"
+        t = torch.tensor(list(payload), dtype=torch.uint8)
+        t = t.cuda(self.device) if on_gpu else t
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(outs, t)
+        return [bytes(o.cpu().tolist()) for o in outs]
+
     # ---- device-side reduction of the engine's total gradient (NCCL through libswb200) ---------------------------
     def _ensure_comm(self):
         import torch
@@ -129,54 +142,58 @@ def slab_route_points(idx0: np.ndarray, nz: int, world_size: int, rank: int) -> 
     return np.nonzero((k >= own.start) & (k < own.stop))[0]
 
 
-class SlabForward3D:
-    """swforward! of ONE 3D acoustic CD shot on a grid cut into z slabs, one per rank (forward only).
+class _SlabSim:
+    """One slab of a z-slab decomposition: the slab-local simulation (owned planes + one ghost plane per interior face) and the routing
+    of sources / receivers to the slab that owns their plane."""
 
-    Every rank passes the global parameters and only ITS slab of the velocity model (`vp_local`, planes
-    slab_local_planes(...), ghost planes included).  Sources / receivers are given with global positions; each is
-    bound on the rank that owns its plane (the others use a muted dummy so that the engine's shot contract holds),
-    and the seismograms are summed over the ranks at the end (every trace is non-zero on exactly one rank).
-    The local sims exchange one plane per interior face and time step over NCCL (swb_sim_set_slab)."""
-
-    def __init__(self, params, vp_local: np.ndarray, sp: "ShotParallel", runparams=None, vp_max_global: Optional[float] = None):
+    def __init__(self, params, vp_local: np.ndarray, world: int, rank: int, device: int, runparams=None, vp_max_global: Optional[float] = None):
         from . import api
         from .types import InputParametersAcoustic, RunParameters, VpAcousticCDMaterialProperties
 
         assert len(params.gridsize) == 3, "z-slab decomposition is for 3D grids"
-        self.sp, self.params = sp, params
+        self.params, self.world, self.rank = params, world, rank
         self.nz = params.gridsize[2]
-        self.loc = slab_local_planes(self.nz, sp.world, sp.rank)
-        self.own = slab_range(self.nz, sp.world, sp.rank)
+        self.loc = slab_local_planes(self.nz, world, rank)
+        self.own = slab_range(self.nz, world, rank)
         assert vp_local.shape == (params.gridsize[0], params.gridsize[1], len(self.loc)), "vp_local must hold this rank's planes (ghost planes included)"
-        T = params.dtype.type
+        self.T = params.dtype.type
         lp = InputParametersAcoustic(params.ntimesteps, params.dt, (params.gridsize[0], params.gridsize[1], len(self.loc)), params.gridspacing, params.boundcond,
                                      dtype=params.dtype)
-        rp = runparams or RunParameters(parall="B200", device=sp.device or 0)
+        rp = runparams or RunParameters(parall="B200", device=device)
         matprop = VpAcousticCDMaterialProperties(np.asfortranarray(vp_local))
         self.sim = api.build_wavesim(lp, matprop, runparams=rp)
         self.sim.set_wavesim_matprop(matprop)
-        vmax = float(np.max(vp_local)) if vp_max_global is None else float(vp_max_global)
-        if vp_max_global is None and sp.world > 1:
-            vmax = sp.allreduce_max(vmax)
-        self.sim._vp_max = T(vmax)  # the C-PML profiles depend on the global maximum velocity (acou_init_bc.jl:13-17)
-        lower, upper = (sp.rank - 1 if sp.rank > 0 else -1), (sp.rank + 1 if sp.rank < sp.world - 1 else -1)
-        if sp.world > 1:
-            sp._ensure_comm()
-        _lib.check(_lib.load().swb_sim_set_slab(self.sim._h, sp._comm, lower, upper))
-        self.T = T
+        self.vmax_local = float(np.max(vp_local))
+        if vp_max_global is not None:
+            self.set_vmax(vp_max_global)
+        self.lower, self.upper = (rank - 1 if rank > 0 else -1), (rank + 1 if rank < world - 1 else -1)
 
-    def forward(self, shot) -> np.ndarray:
-        """runs the shot and returns the full seismogram matrix (nt, nrec) on every rank"""
+    def set_vmax(self, vmax: float) -> None:
+        self.sim._vp_max = self.T(vmax)  # the C-PML profiles depend on the global maximum velocity (acou_init_bc.jl:13-17)
+
+    def set_slab(self, comm) -> None:
+        _lib.check(_lib.load().swb_sim_set_slab(self.sim._h, comm, self.lower, self.upper))
+
+    def export_handle(self) -> "_lib.swb_slab_handle":
+        h = _lib.swb_slab_handle()
+        _lib.check(_lib.load().swb_sim_slab_export(self.sim._h, C.byref(h)))
+        return h
+
+    def connect(self, lower, upper) -> None:
+        _lib.check(_lib.load().swb_sim_slab_connect(self.sim._h, None if lower is None else C.byref(lower), None if upper is None else C.byref(upper)))
+
+    def local_shot(self, shot):
+        """(slab-local shot, indices of the receivers this slab owns)"""
         from . import hostprep
         from .types import ScalarReceivers, ScalarShot, ScalarSources
 
-        T, sim, sp = self.T, self.sim, self.sp
+        T = self.T
         spacing = self.params.gridspacing
         nt = self.params.ntimesteps
         gsrc = hostprep.find_nearest_grid_points(shot.srcs.positions, spacing, T) - 1  # 0-based global indices
         grec = hostprep.find_nearest_grid_points(shot.recs.positions, spacing, T) - 1
-        isrc = slab_route_points(gsrc, self.nz, sp.world, sp.rank)
-        irec = slab_route_points(grec, self.nz, sp.world, sp.rank)
+        isrc = slab_route_points(gsrc, self.nz, self.world, self.rank)
+        irec = slab_route_points(grec, self.nz, self.world, self.rank)
         koff = self.loc.start
 
         def local_positions(gidx, sel):
@@ -191,18 +208,122 @@ class SlabForward3D:
         tf = np.asfortranarray(shot.srcs.tf[:, isrc].astype(T)) if len(isrc) else np.zeros((nt, 1), dtype=T, order="F")
         lshot = ScalarShot(srcs=ScalarSources(local_positions(gsrc, isrc), tf, shot.srcs.domfreq),
                            recs=ScalarReceivers(local_positions(grec, irec), nt, dtype=self.params.dtype))
-        sim.init_shot(lshot)
-        sim.swforward_1shot(lshot)
-        full = np.zeros((nt, grec.shape[0]), dtype=self.params.dtype, order="F")
+        return lshot, irec, grec.shape[0]
+
+    def run(self, lshot, irec, nrec_total) -> np.ndarray:
+        """runs the local shot; returns the (nt, nrec_total) matrix holding this slab's traces (zeros elsewhere)"""
+        self.sim.init_shot(lshot)
+        self.sim.swforward_1shot(lshot)
+        full = np.zeros((self.params.ntimesteps, nrec_total), dtype=self.params.dtype, order="F")
         if len(irec):
             full[:, irec] = lshot.recs.seismograms
+        return full
+
+    def close(self):
+        self.sim.close()
+
+
+class SlabForward3D:
+    """swforward! of ONE 3D acoustic CD shot on a grid cut into z slabs, one per rank (forward only).
+
+    Every rank passes the global parameters and only ITS slab of the velocity model (`vp_local`, planes
+    slab_local_planes(...), ghost planes included).  Sources / receivers are given with global positions; each is
+    bound on the rank that owns its plane (the others use a muted dummy so that the engine's shot contract holds),
+    and the seismograms are summed over the ranks at the end (every trace is non-zero on exactly one rank).
+    exchange = "p2p" (default): the step kernels store the boundary planes straight into the neighbours' ghost planes over NVLink
+    (IPC-mapped peer memory, per-step flags; swb_sim_slab_export / swb_sim_slab_connect); "nccl": grouped ncclSend / ncclRecv of
+    one plane per interior face after every step."""
+
+    def __init__(self, params, vp_local: np.ndarray, sp: "ShotParallel", runparams=None, vp_max_global: Optional[float] = None, exchange: str = "p2p"):
+        import os
+
+        self.sp, self.params = sp, params
+        self.slab = _SlabSim(params, vp_local, sp.world, sp.rank, sp.device or 0, runparams, vp_max_global)
+        self.sim, self.loc, self.own, self.T, self.nz = self.slab.sim, self.slab.loc, self.slab.own, self.slab.T, self.slab.nz
+        if vp_max_global is None:
+            self.slab.set_vmax(sp.allreduce_max(self.slab.vmax_local) if sp.world > 1 else self.slab.vmax_local)
+        exchange = os.environ.get("SWB_SLAB_EXCHANGE", exchange)
+        assert exchange in ("p2p", "nccl")
+        self.exchange = exchange if sp.world > 1 else "none"
+        if sp.world > 1 and exchange == "nccl":
+            sp._ensure_comm()
+        self.slab.set_slab(sp._comm if exchange == "nccl" else None)
+        if sp.world > 1 and exchange == "p2p":
+            handles = sp.allgather_bytes(bytes(self.slab.export_handle()))
+            hs = [_lib.swb_slab_handle.from_buffer_copy(b) for b in handles]
+            self.slab.connect(hs[sp.rank - 1] if sp.rank > 0 else None, hs[sp.rank + 1] if sp.rank < sp.world - 1 else None)
+
+    def forward(self, shot) -> np.ndarray:
+        """runs the shot and returns the full seismogram matrix (nt, nrec) on every rank"""
+        sp = self.sp
+        lshot, irec, nrec = self.slab.local_shot(shot)
+        full = self.slab.run(lshot, irec, nrec)
         if sp.world > 1:
             full = sp.allreduce_host({"s": full})[0]["s"]
         shot.recs.seismograms[...] = full
         return full
 
     def exchange_mode(self) -> str:
-        return "grouped ncclSend/ncclRecv of one plane per interior face on the engine's stream after every step" if self.sp.world > 1 else "none (single slab)"
+        return {"p2p": "boundary planes stored by the step kernels straight into the neighbours' ghost planes (IPC-mapped peer memory over NVLink), "
+                       "stream-ordered 32-bit flags keep neighbouring slabs within one step; no collective in the time loop",
+                "nccl": "grouped ncclSend/ncclRecv of one plane per interior face on the engine's stream after every step",
+                "none": "none (single slab)"}[self.exchange]
 
     def close(self):
-        self.sim.close()
+        self.slab.close()
+
+
+class SlabForwardLocal:
+    """The same decomposition driven from ONE process: `nslabs` slab simulations on the given devices (all on device 0 by default), one host
+    thread per slab for the duration of a shot (a slab's forward call blocks until its neighbours have caught up), the halo exchange
+    through peer memory only.  This is the shape of the Julia integration (one process, one task per GPU); on a single GPU it runs
+    the whole exchange protocol -- ghost planes, peer stores, flags -- without needing a second device."""
+
+    def __init__(self, params, vp: np.ndarray, nslabs: int, devices: Optional[Sequence[int]] = None, runparams_for=None):
+        from .types import RunParameters
+
+        self.params, self.n = params, nslabs
+        nz = params.gridsize[2]
+        devices = list(devices) if devices is not None else [0] * nslabs
+        vmax = float(np.max(vp))
+        self.slabs = []
+        for r in range(nslabs):
+            loc = slab_local_planes(nz, nslabs, r)
+            rp = runparams_for(devices[r]) if runparams_for is not None else RunParameters(parall="B200", device=devices[r], erroronPPW=False)
+            self.slabs.append(_SlabSim(params, np.asfortranarray(vp[:, :, loc.start:loc.stop]), nslabs, r, devices[r], rp, vmax))
+        for s in self.slabs:
+            s.set_slab(None)
+        hs = [s.export_handle() for s in self.slabs] if nslabs > 1 else []
+        for r, s in enumerate(self.slabs):
+            if nslabs > 1:
+                s.connect(hs[r - 1] if r > 0 else None, hs[r + 1] if r < nslabs - 1 else None)
+
+    def forward(self, shot) -> np.ndarray:
+        import threading
+
+        prepared = [s.local_shot(shot) for s in self.slabs]
+        out, err = [None] * self.n, [None] * self.n
+
+        def work(r):
+            try:
+                out[r] = self.slabs[r].run(*prepared[r])
+            except Exception as e:  # noqa: BLE001
+                err[r] = e
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(self.n)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in err:
+            if e is not None:
+                raise e
+        full = out[0]
+        for o in out[1:]:
+            full = full + o
+        shot.recs.seismograms[...] = full
+        return full
+
+    def close(self):
+        for s in self.slabs:
+            s.close()

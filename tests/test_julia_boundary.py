@@ -99,7 +99,7 @@ def test_ctypes_structures_match_the_library_layout(layout):
 
 
 # ---- Julia structs -----------------------------------------------------------------------------------------------------
-PRIM = {"Int32": (4, 4), "Int64": (8, 8), "Float64": (8, 8), "Float32": (4, 4), "Cdouble": (8, 8), "Csize_t": (8, 8), "UInt8": (1, 1)}
+PRIM = {"Int32": (4, 4), "Int64": (8, 8), "UInt64": (8, 8), "Float64": (8, 8), "Float32": (4, 4), "Cdouble": (8, 8), "Csize_t": (8, 8), "UInt8": (1, 1)}
 
 
 def jl_structs(src):
