@@ -567,10 +567,13 @@ def slab_entry(S, torch, dist, world, rank, local):
     import slab_check
 
     try:
-        ok, detail = slab_check.bitwise_twin(S, torch, dist, world, rank, local)
-        res = slab_check.throughput(S, torch, dist, world, rank, local, grid=(2048, 2048, 128 * world), nt=100)
-        res["bitwise_equal_to_single_gpu_on_twin"] = bool(ok)
-        res["twin"] = detail
+        ok, detail = slab_check.bitwise_twin(S, torch, dist, world, rank, local, exchange="p2p")
+        ok2, detail2 = slab_check.bitwise_twin(S, torch, dist, world, rank, local, twins=slab_check.TWINS[:1], exchange="nccl")
+        res = slab_check.throughput(S, torch, dist, world, rank, local, grid=(2048, 2048, 128 * world), nt=100, exchange="p2p")
+        alt = slab_check.throughput(S, torch, dist, world, rank, local, grid=(2048, 2048, 128 * world), nt=100, exchange="nccl")
+        res["bitwise_equal_to_single_gpu_on_twin"] = bool(ok and ok2)
+        res["twin"] = detail + detail2
+        res["nccl_exchange_for_comparison"] = {k: alt[k] for k in ("ms_per_step", "value", "per_gpu_Gcell_per_s", "exchange")}
         return res
     except Exception as e:  # noqa: BLE001 -- the headline line must survive a failing extra
         return {"error": str(e)[:300]}
@@ -583,9 +586,10 @@ def other_configs(peak):
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import bench_sim
 
-    runs = [("C3 elastic P-SV 4096x2048 Float32 (f32 arithmetic)", ["--kind ela --n 4096 2048 --nt 60 --check-freq 10 --dtype f32 --fast-f32 1 --nrec 10 --reps 2"]),
-            ("C3 elastic P-SV 4096x2048 Float32 (f64 intermediates, reference-faithful)", ["--kind ela --n 4096 2048 --nt 60 --check-freq 10 --dtype f32 --fast-f32 0 --nrec 10 --reps 2"]),
-            ("C3 elastic P-SV 4096x2048 Float64", ["--kind ela --n 4096 2048 --nt 60 --check-freq 10 --dtype f64 --nrec 10 --reps 2"]),
+    c3 = "C3 2D elastic P-SV 4096x2048, nt=1000, check_freq=31, off-grid moment-tensor source, 10 vector receivers, forward + rho/lambda/mu adjoint gradient"
+    runs = [(c3 + " -- Float32 (f32 arithmetic)", ["--kind ela --n 4096 2048 --nt 1000 --check-freq 31 --dtype f32 --fast-f32 1 --nrec 10 --reps 1"]),
+            (c3 + " -- Float32 (f64 intermediates, reference-faithful)", ["--kind ela --n 4096 2048 --nt 1000 --check-freq 31 --dtype f32 --fast-f32 0 --nrec 10 --reps 1"]),
+            (c3 + " -- Float64", ["--kind ela --n 4096 2048 --nt 1000 --check-freq 31 --dtype f64 --nrec 10 --reps 1"]),
             ("2D acoustic CD 4096x4096 Float32 (C1 physics at roofline size)", ["--kind cd --n 4096 4096 --nt 100 --check-freq 10 --reps 2"]),
             ("C4 3D acoustic CD 768^3 Float32, forward + adjoint gradient, nt=500, check_freq=50, 1024 receivers",
              ["--kind cd --n 768 768 768 --nt 500 --check-freq 50 --nrec 1024 --reps 1", "--kind cd --n 768 768 768 --nt 60 --check-freq 10 --nrec 1024 --reps 1"])]

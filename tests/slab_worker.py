@@ -23,10 +23,12 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
-    ok, detail = slab_check.bitwise_twin(S, torch, dist, world, rank, local)
+    ok, detail = slab_check.bitwise_twin(S, torch, dist, world, rank, local, exchange="p2p")
+    ok2, detail2 = slab_check.bitwise_twin(S, torch, dist, world, rank, local, exchange="nccl")
+    ok, detail = ok and ok2, detail + detail2
     if rank == 0:
         for d in detail:
-            print(f"slab test {d['dtype']} fast={d['fast_f32']} n={tuple(d['grid'])} world={world}: bitwise equal = {d['bitwise_equal']}, live traces = {d['live_traces']}", flush=True)
+            print(f"slab test [{d['exchange']}] {d['dtype']} fast={d['fast_f32']} n={tuple(d['grid'])} world={world}: bitwise equal = {d['bitwise_equal']}, live traces = {d['live_traces']}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -13,7 +13,7 @@ import numpy as np
 TWINS = [(np.float32, False, (70, 52, 90), 6, True), (np.float64, False, (64, 40, 61), 5, False), (np.float32, True, (140, 36, 75), 7, True)]
 
 
-def bitwise_twin(S, torch, dist, world, rank, local, twins=TWINS, nt=160):
+def bitwise_twin(S, torch, dist, world, rank, local, twins=TWINS, nt=160, exchange="p2p"):
     from swb200.multigpu import ShotParallel, SlabForward3D, slab_local_planes
 
     ok, detail = True, []
@@ -46,7 +46,7 @@ def bitwise_twin(S, torch, dist, world, rank, local, twins=TWINS, nt=160):
         sp = ShotParallel(device=local)
         rp = S.RunParameters(parall="B200", device=local, erroronPPW=False, fast_f32=fast)
         loc = slab_local_planes(nz, world, rank)
-        slab = SlabForward3D(params, np.asfortranarray(vp[:, :, loc.start:loc.stop]), sp, runparams=rp)
+        slab = SlabForward3D(params, np.asfortranarray(vp[:, :, loc.start:loc.stop]), sp, runparams=rp, exchange=exchange)
         got = slab.forward(shot())
         got2 = slab.forward(shot())  # a second shot on the same sims: replays whatever the first one set up
         slab.close()
@@ -56,7 +56,7 @@ def bitwise_twin(S, torch, dist, world, rank, local, twins=TWINS, nt=160):
             ref = ref_shot.recs.seismograms
             same = bool(np.array_equal(got, ref) and np.array_equal(got2, ref))
             live = int(np.count_nonzero(np.max(np.abs(ref), axis=0)))
-            detail.append({"dtype": np.dtype(dtype).name, "fast_f32": fast, "grid": list(n), "nt": nt, "bitwise_equal": same, "live_traces": f"{live}/{nrec}"})
+            detail.append({"exchange": exchange, "dtype": np.dtype(dtype).name, "fast_f32": fast, "grid": list(n), "nt": nt, "bitwise_equal": same, "live_traces": f"{live}/{nrec}"})
             ok = ok and same and live == nrec
         sp.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
@@ -64,7 +64,7 @@ def bitwise_twin(S, torch, dist, world, rank, local, twins=TWINS, nt=160):
     return bool(int(flag.item()) == 1), detail
 
 
-def throughput(S, torch, dist, world, rank, local, grid=(2048, 2048, 1024), nt=100, halo=20, fast_f32=True, reps=2):
+def throughput(S, torch, dist, world, rank, local, grid=(2048, 2048, 1024), nt=100, halo=20, fast_f32=True, reps=2, exchange="p2p"):
     from swb200.multigpu import ShotParallel, SlabForward3D, slab_local_planes
 
     T = np.float32
@@ -80,7 +80,7 @@ def throughput(S, torch, dist, world, rank, local, grid=(2048, 2048, 1024), nt=1
     params = S.InputParametersAcoustic(nt, T(dt), (nx, ny, nz), (T(h),) * 3, bc, dtype=np.dtype(T))
     sp = ShotParallel(device=local)
     rp = S.RunParameters(parall="B200", device=local, erroronPPW=False, fast_f32=bool(fast_f32))
-    slab = SlabForward3D(params, vp, sp, runparams=rp, vp_max_global=vmax)
+    slab = SlabForward3D(params, vp, sp, runparams=rp, vp_max_global=vmax, exchange=exchange)
     f0 = 8.0
     t = np.arange(nt) * dt
     tf = np.asfortranarray((1000.0 * S.rickerstf(t, 1.2 / f0, f0)).astype(T).reshape(nt, 1))
