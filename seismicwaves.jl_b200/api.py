@@ -92,8 +92,8 @@ class WaveSimulation:
     # ---- checks mirrored from the reference ---------------------------------------------------------
     _cfl_factor = 1.0
 
-    def check_courant_condition(self, vp: np.ndarray) -> None:
-        """acou_models.jl:5-17 / 240-251 (7/6 for the 4th-order staggered stencils)."""
+    def check_courant_condition(self, vp) -> None:
+        """acou_models.jl:5-17 / 240-251 (7/6 for the 4th-order staggered stencils); vp: the model or its maximum."""
         vel_max = float(np.max(vp))
         tmp = math.sqrt(sum(1.0 / float(s) ** 2 for s in self.spacing))
         courant = vel_max * float(self.dt) * tmp * self._cfl_factor
@@ -281,10 +281,11 @@ class AcousticCDCPMLWaveSimulation(_AcousticBase):
         vp = matprop.vp
         assert vp.ndim == self.N, "Material property dimensionality must be the same as the wavesim!"
         assert vp.shape == self.gridsize, f"Material property number of grid points must be the same as the wavesim! \n {vp.shape}, {self.gridsize}"
-        assert np.all(vp > 0), "Pressure velocity material property must be positive!"
-        self.check_courant_condition(vp)
+        vmin, vmax = np.min(vp), np.max(vp)  # one pass each; every check below derives from them
+        assert vmin > 0, "Pressure velocity material property must be positive!"
+        self.check_courant_condition(vmax)
         self.matprop = VpAcousticCDMaterialProperties(vp.copy(order="F"))
-        self._vp_min, self._vp_max = float(np.min(vp)), self.T(np.max(vp))  # reductions over the model once per update, not per shot
+        self._vp_min, self._vp_max = float(vmin), self.T(vmax)  # reductions over the model once per update, not per shot
         arr = (C.c_void_p * 1)(self.matprop.vp.ctypes.data)
         _lib.check(self.lib.swb_sim_set_material(self._h, 1, arr, 0))
 
@@ -312,11 +313,12 @@ class AcousticVDStaggeredCPMLWaveSimulation(_AcousticBase):
         vp, rho = matprop.vp, matprop.rho
         assert vp.ndim == rho.ndim == self.N, "Material property dimensionality must be the same as the wavesim!"
         assert vp.shape == rho.shape == self.gridsize, f"Material property number of grid points must be the same as the wavesim! \n {vp.shape}, {rho.shape}, {self.gridsize}"
-        assert np.all(vp > 0), "Pressure velocity material property must be positive!"
-        assert np.all(rho > 0), "Density material property must be positive!"
-        self.check_courant_condition(vp)
+        vmin, vmax = np.min(vp), np.max(vp)  # one pass each; every check below derives from them
+        assert vmin > 0, "Pressure velocity material property must be positive!"
+        assert np.min(rho) > 0, "Density material property must be positive!"
+        self.check_courant_condition(vmax)
         self.matprop = VpRhoAcousticVDMaterialProperties(vp.copy(order="F"), rho.copy(order="F"), interp_method=matprop.interp_method)
-        self._vp_min, self._vp_max = float(np.min(vp)), self.T(np.max(vp))
+        self._vp_min, self._vp_max = float(vmin), self.T(vmax)
         arr = (C.c_void_p * 2)(self.matprop.vp.ctypes.data, self.matprop.rho.ctypes.data)
         _lib.check(self.lib.swb_sim_set_material(self._h, 2, arr, 0 if matprop.interp_method == "arithmetic" else 1))
 
