@@ -126,6 +126,9 @@ end
 Base.Broadcast.materialize!(dest::SubArray{T, 1, <:B200Array{T, 1}, Tuple{UnitRange{Int}}}, bc::Base.Broadcast.Broadcasted{<:Any, <:Any, typeof(identity), <:Tuple{Number}}) where {T} =
     fillrange!(parent(dest), dest.indices[1], bc.args[1])
 Base.Broadcast.materialize!(dest::B200Array, bc::Base.Broadcast.Broadcasted{<:Any, <:Any, typeof(identity), <:Tuple{Number}}) = fill!(dest, bc.args[1])
+# `dest .= x` reaches materialize! with the bare scalar first (Base.broadcasted(identity, x::Number) === x): catch that form too
+Base.Broadcast.materialize!(dest::B200Array, x::Number) = fill!(dest, x)
+Base.Broadcast.materialize!(dest::SubArray{T, 1, <:B200Array{T, 1}, Tuple{UnitRange{Int}}}, x::Number) where {T} = fillrange!(parent(dest), dest.indices[1], x)
 
 # ---------------------------------------------------------------------------------------------------------------------
 # C structs of include/swb200.h (layout must match field for field; checked by tests/test_julia_boundary.py)
