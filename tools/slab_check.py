@@ -17,11 +17,14 @@ def bitwise_twin(S, torch, dist, world, rank, local, twins=TWINS, nt=160, exchan
     from swb200.multigpu import ShotParallel, SlabForward3D, slab_local_planes
 
     ok, detail = True, []
+    nt0 = nt
     for dtype, fast, n, halo, freetop in twins:
         T = np.dtype(dtype).type
         rng = np.random.default_rng(5)
+        nz0 = n[2]
         n = (n[0], n[1], max(n[2], (2 * halo + 6) * world))  # every slab-local grid must still hold the reference's minimum of 2 halo + 3 planes
         nx, ny, nz = n
+        nt = int(round(nt0 * nz / nz0))  # ... and the wavefield still has to reach every receiver
         h = 10.0
         vp = 1800.0 + 1500.0 * (np.arange(nz) / (nz - 1))[None, None, :] + rng.normal(0, 30.0, size=n)
         vp = np.asfortranarray(vp.astype(T))
