@@ -255,7 +255,8 @@ template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
 __global__ void __launch_bounds__(HAS_Y ? 32 * CDF_TY : 32 * CDF_W2D, HAS_Y ? (sizeof(CT) == 4 ? (ADJ ? 3 : 4) : 2) : (sizeof(CT) == 4 ? 8 : 4))
     cd_bulk_kernel(const CdFusedParams<T> P)
 {
-    cd_bulk_body<T, CT, HAS_Y, ADJ, FMA>(P, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)gridDim.x, (int)gridDim.y, (int)blockDim.y, (int)threadIdx.x,
+    const int bz = P.rev ? (int)gridDim.z - 1 - (int)blockIdx.z : (int)blockIdx.z;
+    cd_bulk_body<T, CT, HAS_Y, ADJ, FMA>(P, (int)blockIdx.x, (int)blockIdx.y, bz, (int)gridDim.x, (int)gridDim.y, (int)blockDim.y, (int)threadIdx.x,
                                          (int)threadIdx.y);
 }
 
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? 8 : 4) cd_merged2
 {
     const int b = (int)blockIdx.x;
     if (b < nbulk)
-        cd_bulk_body<T, CT, false, ADJ, FMA>(P, b % gdx, 0, b / gdx, gdx, 1, CDF_W2D, (int)threadIdx.x & 31, (int)threadIdx.x >> 5);
+        cd_bulk_body<T, CT, false, ADJ, FMA>(P, b % gdx, 0, P.rev ? nbulk / gdx - 1 - b / gdx : b / gdx, gdx, 1, CDF_W2D, (int)threadIdx.x & 31, (int)threadIdx.x >> 5);
     else
         cd_rim_body<T, CT, false, ADJ, FMA>(P, b - nbulk, (int)threadIdx.x);
 }

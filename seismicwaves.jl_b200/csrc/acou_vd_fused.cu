@@ -389,13 +389,17 @@ __device__ __forceinline__ void vd_edge_p(const VdCtx<T> &C, const int r, const 
 
 // Tile rows are issued bottom strip rows first, then from the top: the rows that touch the bottom C-PML strip run the slow
 // generic body and would otherwise form a tail of long CTAs at the end of the grid.
+// Serpentine sweep (rev = 1 on every other launch): the remaining rows are issued in descending order, so a launch starts where
+// the previous one ended -- on the rows whose fields (written or read a moment ago) and material factors still sit in the 126 MB L2.
 template <int TY>
-__device__ __forceinline__ int vd_tile_row(int halo)
+__device__ __forceinline__ int vd_tile_row(int halo, int rev)
 {
     const int nty = (int)gridDim.y;
     const int nedge = min(nty, (halo + 6 + TY + TY - 1) / TY);
-    const int by = (int)blockIdx.y + nty - nedge;
-    return by >= nty ? by - nty : by;
+    const int b = (int)blockIdx.y;
+    if (b < nedge)
+        return nty - nedge + b;
+    return rev ? nty - 1 - b : b - nedge;
 }
 
 template <class T, class CT, bool ADJ, int TY, bool edge>
@@ -408,7 +412,7 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
     T *svy = sm + L::VY_OFF, *sm1y = sm + L::M1Y_OFF, *spi = sm + L::PI_OFF + SW + 8;
 
     const int tid = threadIdx.x;
-    const int trow = vd_tile_row<TY>(P.halo);
+    const int trow = vd_tile_row<TY>(P.halo, P.rev);
     const int x0 = blockIdx.x * TX, y0 = trow * TY;
     const int nx = P.nx, ny = P.ny, h = P.halo;
     const long long ld = P.ld;
@@ -565,7 +569,7 @@ __device__ __forceinline__ void vd_tile_interior(const VdFusedParams<T> &P, unsi
     T *svy = sm + L::VY_OFF, *sm1y = sm + L::M1Y_OFF, *spi = sm + L::PI_OFF + SW + 8;
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int trow = vd_tile_row<TY>(P.halo);
+    const int trow = vd_tile_row<TY>(P.halo, P.rev);
     const int x0 = blockIdx.x * TX, y0 = trow * TY;
     const long long ld = P.ld;
     const int tile = trow * gridDim.x + blockIdx.x;
@@ -716,7 +720,7 @@ template <class T, class CT, bool ADJ, int TY>
 __global__ void __launch_bounds__(NTHR, sizeof(T) == 4 ? (ADJ ? 3 : 4) : 1) vd_fused_kernel(const __grid_constant__ VdFusedParams<T> P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int x0 = blockIdx.x * TX, y0 = vd_tile_row<TY>(P.halo) * TY, h = P.halo;
+    const int x0 = blockIdx.x * TX, y0 = vd_tile_row<TY>(P.halo, P.rev) * TY, h = P.halo;
     // block-uniform: does the tile (with the halo it recomputes) touch a C-PML strip or the grid edge?
     const bool edge = (x0 - 8 <= h + 2) || (x0 + TX + 8 >= P.nx - h - 2) || (y0 - 4 <= h + 2) || (y0 + TY + 4 >= P.ny - h - 2);
     if (edge && !P.dbg_all_interior)

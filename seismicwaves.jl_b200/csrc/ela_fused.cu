@@ -592,11 +592,12 @@ __device__ __forceinline__ void disp_task(const TileCtx<T, TZ, ADJ> &C, const in
 // Tile rows are issued bottom strip rows first, then from the top: the rows that touch the bottom C-PML strip run the slow
 // per-cell body and would otherwise form a tail of long CTAs at the end of the grid.
 template <int TZ>
-__device__ __forceinline__ int tile_row(int halo, int nty, int brow)
+__device__ __forceinline__ int tile_row(int halo, int nty, int brow, int rev)
 {
     const int nedge = min(nty, (halo + TZ + 3 + TZ - 1) / TZ);
-    const int by = brow + nty - nedge;
-    return by >= nty ? by - nty : by;
+    if (brow < nedge)
+        return nty - nedge + brow;
+    return rev ? nty - 1 - brow : brow - nedge; // serpentine: every other launch walks the remaining rows upwards
 }
 
 template <class T, class CT, int TZ, bool ADJ, bool EDGE>
@@ -812,7 +813,7 @@ __global__ void __launch_bounds__(NTHR, (PART == 1 && !ADJ && sizeof(T) == 4 && 
         }
     } else {
         bx = (int)blockIdx.x;
-        trow = tile_row<TZ>(P.halo, P.ntz, (int)blockIdx.y);
+        trow = tile_row<TZ>(P.halo, P.ntz, (int)blockIdx.y, P.rev);
     }
     // interior tile: every cell of the tile's stress region (1-based indices x0-1 .. x0+TX+2, z0-1 .. z0+TZ+2) lies inside all
     // update ranges, outside every C-PML strip and below the free-surface rows (host: ela_interior_range)

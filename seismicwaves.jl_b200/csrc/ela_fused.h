@@ -65,6 +65,7 @@ struct ElaFusedParams {
     T *g_ri, *g_rj, *g_l, *g_m, *g_mh;
     T inv_dt2;
     int dbg_all_interior; // timing experiment only (SWB_ELF_DEBUG_ALL_INTERIOR=1): wrong results in the strips
+    int rev;              // 1: tile rows after the edge rows in descending order (serpentine sweep: a launch starts on the rows the previous one left in L2)
 };
 
 // st_edge != nullptr: the interior tiles and the edge tiles (C-PML strips, grid edges, free surface) run as two kernels, the edge

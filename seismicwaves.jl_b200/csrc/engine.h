@@ -153,6 +153,10 @@ class SimBase {
     template <class F>
     void run_graph(Graph &g, F &&enqueue);
     void drop_graph(Graph &g);
+    // Keep [base, base + bytes) resident in the persisting part of the L2 for every kernel launched on `st` (access-policy window, hit
+    // ratio scaled to what the device lets us set aside): a time-invariant array every step re-reads -- a material factor plane -- then
+    // stops costing HBM bandwidth.  Opt-in experiment (SWB_L2_PERSIST=1): measured slower on B200, see engine_core.cu; returns 0 when off.
+    size_t l2_persist(cudaStream_t st, const void *base, size_t bytes);
     void upload(void *dst, const void *src, size_t bytes);
     void download(void *dst, const void *src, size_t bytes);
     void d2d(void *dst, const void *src, size_t bytes);

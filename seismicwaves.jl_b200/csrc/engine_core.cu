@@ -1,6 +1,7 @@
 // engine_core.cu -- device memory, checkpoint storage and the parts of the per-shot engine that do not
 // depend on the physics.
 #include "engine.h"
+#include <cstdlib>
 #include <cuda.h>
 #include <algorithm>
 #include <cstring>
@@ -366,6 +367,38 @@ void SimBase::download(void *dst, const void *src, size_t bytes)
         return;
     SWB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
     SWB_CUDA(cudaStreamSynchronize(stream));
+}
+
+size_t SimBase::l2_persist(cudaStream_t st, const void *base, size_t bytes)
+{
+    // Measured on B200 (tools/ab_l2persist.sh, VD 4096^2): pinning fact_m0 in 79 MB of persisting L2 makes the step SLOWER (forward
+    // 107 -> 166 us, adjoint 190 -> 306 us; 48 MB: 108 / 194 us) -- the streaming traffic needs the L2 as its staging buffer more than
+    // it gains from one resident array.  Kept as an opt-in experiment (SWB_L2_PERSIST=1), off by default.
+    static const bool on = std::getenv("SWB_L2_PERSIST") != nullptr;
+    if (!on || bytes == 0)
+        return 0;
+    use_device();
+    int max_persist = 0, max_window = 0;
+    SWB_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, desc.device));
+    SWB_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, desc.device));
+    if (max_persist <= 0 || max_window <= 0)
+        return 0;
+    size_t want = (size_t)max_persist;
+    if (const char *e = std::getenv("SWB_L2_PERSIST_MB"))
+        want = std::min<size_t>(want, (size_t)std::atoll(e) << 20);
+    SWB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+    size_t got = 0;
+    SWB_CUDA(cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize));
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof(attr));
+    const size_t win = std::min(bytes, (size_t)max_window);
+    attr.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)got / (double)win);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    SWB_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return std::min(got, win);
 }
 
 void SimBase::d2d(void *dst, const void *src, size_t bytes)

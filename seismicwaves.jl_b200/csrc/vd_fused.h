@@ -51,6 +51,7 @@ struct VdFusedParams {
     const T *pc_it, *pc_itm1;
     T *g0, *g1x, *g1y;
     int dbg_all_interior; // timing experiment only (SWB_VD_DEBUG_ALL_INTERIOR=1): wrong results in the strips
+    int rev;              // 1: the tile rows after the edge rows are issued in descending order (serpentine sweep, see vd_tile_row)
 };
 
 template <class T>
