@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswb200.so")
+LIB_PATH = os.environ.get("SWB200_LIB") or os.path.join(_HERE, "libswb200.so")  # SWB200_LIB: a differently built library (experiments)
 
 SWB_F32, SWB_F64 = 0, 1
 SWB_ACOU_CD, SWB_ACOU_VD, SWB_ELA_ISO = 1, 2, 3

@@ -348,6 +348,8 @@ __device__ __forceinline__ void cd_axis_term_vec(CT (&term)[V], const CT (&w1)[2
     stv<T, V>(xi + (long long)(ii - 1) * stride, xo);
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
 __device__ __forceinline__ void cd_rim_body(const CdFusedParams<T> &P, const int cta, const int tid)
 {
@@ -373,6 +375,33 @@ __device__ __forceinline__ void cd_rim_body(const CdFusedParams<T> &P, const int
     const long long ld = P.ld, plane = P.plane;
     const long long off = (long long)k * plane + (long long)j * ld + i0;
 
+    // The memory variables of a strip cell are addressed by indices only, but their loads sit behind the first use of the pressure
+    // values in program order (three dependent batches of DRAM latency per thread, ncu: the stalls sit on the first use of each
+    // batch): ask for their lines now, so that those loads hit the L1 when the code reaches them.
+    if (h > 0 && P.rim_prefetch) {
+        const int sz = strip_index(k + 1, nz, h);
+        if (sz >= 2 && (sz <= h ? P.zpml_lo != 0 : P.zpml_hi != 0) && sz <= 2 * h) {
+            const long long o = (long long)j * ld + i0, st = ld * ny;
+            prefetch_l1(P.psi_in[2] + o + (long long)(sz - 1) * st);
+            prefetch_l1(P.psi_in[2] + o + (long long)(sz - 2) * st);
+            prefetch_l1(P.xi[2] + o + (long long)(sz - 1) * st);
+        }
+        if (HAS_Y) {
+            const int sy = strip_index(j + 1, ny, h);
+            if (sy >= 2 && sy <= 2 * h) {
+                const long long o = (long long)k * ld * (2 * h) + i0, ox = (long long)k * ld * (2 * (h + 1)) + i0;
+                prefetch_l1(P.psi_in[1] + o + (long long)(sy - 1) * ld);
+                prefetch_l1(P.psi_in[1] + o + (long long)(sy - 2) * ld);
+                prefetch_l1(P.xi[1] + ox + (long long)(sy - 1) * ld);
+            }
+        }
+        if (i0 + 1 <= h || i0 + V >= nx - h + 1) {
+            const long long jk = (long long)k * ny + j;
+            const int sx = max(2, strip_index(i0 + 1 <= h ? i0 + 1 : min(i0 + V, nx), nx, h));
+            prefetch_l1(P.psi_in[0] + jk * (2 * h) + min(sx - 2, 2 * h - 1));
+            prefetch_l1(P.xi[0] + jk * (2 * (h + 1)) + min(sx - 1, 2 * h + 1));
+        }
+    }
     VT out = ldv<T, V>(P.pold + off); // faces (and pitch padding) keep pold
     VT c2 = {}, c1 = {}, c0 = {}, g = {};
     if (ADJ) {
@@ -462,8 +491,11 @@ __device__ __forceinline__ void cd_rim_body(const CdFusedParams<T> &P, const int
     }
 }
 
+#ifndef CDF_RIM_MINB
+#define CDF_RIM_MINB 8
+#endif
 template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
-__global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? 8 : 4) cd_rim_kernel(const CdFusedParams<T> P)
+__global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? CDF_RIM_MINB : CDF_RIM_MINB / 2) cd_rim_kernel(const CdFusedParams<T> P)
 {
     cd_rim_body<T, CT, HAS_Y, ADJ, FMA>(P, (int)blockIdx.x, (int)threadIdx.x);
 }

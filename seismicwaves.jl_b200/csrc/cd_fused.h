@@ -41,6 +41,7 @@ struct CdFusedParams {
     // nz - 1 is a ghost plane the neighbour owns; this slab's kernels leave it alone.
     T *peer_lo, *peer_hi;
     int ghost_lo, ghost_hi;
+    int rim_prefetch; // 1: rim threads prefetch their C-PML memory variables before the first dependent use
     int rev; // 1: the bulk z chunks are issued from the last to the first (serpentine sweep: a step starts on the planes the previous one left in L2)
     long long ld, plane;   // row pitch and plane pitch (elements) of pcur / pold / pnew / fact / grad / stored fields
     T inv_d[3];            // 1 / spacing along kernel axes x, y, z
