@@ -133,16 +133,16 @@ class ClockSampler:
 # (separate p / inject / v / record / correlate passes).  Julia is not installed, so the
 # reference itself cannot run (kind = "port").
 # ---------------------------------------------------------------------------------------------------------
-def cpu_sample_problem(n=4096, nt=60, cf=7):
+def cpu_sample_problem(n=4096, nt=40, cf=6):
     """the C2 problem itself (grid, model, halo, free surface, 512 receivers) with the time axis shortened so that one shot's
-    gradient costs the host ~10 s: nt = 60, check_freq = isqrt(60) = 7"""
+    gradient costs the host a few seconds (the driver times 25 of them): nt = 40, check_freq = isqrt(40) = 6"""
     prob = c2_problem(n=n, nt=nt, nshots_total=64, nrec=512)
     prob["check_freq"] = cf
     return prob
 
 
 CPU_SAMPLE = ("per step: one shot's gradient of the C2 workload itself (4096x4096 Float32 model, halo 20, free surface, 1 source, 512 receivers, "
-              "L2 misfit vs zeros) with the time axis shortened to nt=60, check_freq=7")
+              "L2 misfit vs zeros) with the time axis shortened to nt=40, check_freq=6")
 
 
 def cpu_threads() -> int:
@@ -230,7 +230,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(None, args, note="the CPU arm runs this workload with the time axis shortened (nt=60, check_freq=7): same grid, model, "
+        "data": "synthetic", "config": workload_config(None, args, note="the CPU arm runs this workload with the time axis shortened (nt=40, check_freq=6): same grid, model, "
                                                                        "boundaries, sources and receivers; the metric is a rate (cell-updates/s), so the step count does not enter it"),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
