@@ -671,18 +671,29 @@ function SeismicWaves.run_swgradient!(wavesim::Vector{<:Union{AcousticCDCPMLWave
     grpshots = SeismicWaves.distribsrcs(nshots, ndev)      # ndev <= nshots: exactly ndev non-empty contiguous groups
     misfitvals = Base.zeros(T, nshots)
     compute_misfit = wavesim[1].gradparams.compute_misfit
-    # phase 1 (no collective inside): every rank computes its shots; an exception is kept, not thrown, so that no rank is left
-    # alone in a collective
+    # engines first, one after the other: a failure here (no device, out of memory) is thrown before any rank enters a collective
+    handles = [engine(w) for w in wavesim[1:ndev]]
+    # phase 0: the communicator (ncclCommInitRank is itself a collective: every rank enters it, nothing else can fail before it)
     comms = fill(C_NULL, ndev)
     errors = Vector{Any}(nothing, ndev)
+    if ndev > 1
+        tasks = map(1:ndev) do r
+            Threads.@spawn try
+                comm = Ref{Ptr{Cvoid}}(C_NULL)
+                check(ccall((:swb_comm_create, lib), Int32, (Ptr{UInt8}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), id, ndev, r - 1, device_of(wavesim[r]), comm))
+                comms[r] = comm[]
+            catch err
+                errors[r] = err
+            end
+        end
+        foreach(wait, tasks)
+    end
+    # phase 1 (no collective inside): every rank computes its shots; an exception is kept, not thrown, so that no rank is left
+    # alone in a collective
     tasks = map(1:ndev) do r
         Threads.@spawn try
-            model, h = wavesim[r], engine(wavesim[r])
-            if ndev > 1
-                comm = Ref{Ptr{Cvoid}}(C_NULL)
-                check(ccall((:swb_comm_create, lib), Int32, (Ptr{UInt8}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), id, ndev, r - 1, device_of(model), comm))
-                comms[r] = comm[]
-            end
+            errors[r] === nothing || return
+            model, h = wavesim[r], handles[r]
             upload_material!(model)
             check(ccall((:swb_sim_zero_total_gradient, lib), Int32, (Ptr{Cvoid},), h))
             for s in grpshots[r]

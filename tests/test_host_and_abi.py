@@ -138,3 +138,29 @@ def test_julia_extension_binds_only_exported_symbols():
     assert len(bound) >= 20, bound
     missing = [s for s in bound if s not in S._lib.EXPORTS or not hasattr(lib, s)]
     assert not missing, missing
+
+
+def test_header_is_valid_c_and_layout_matches_a_c_compiler(tmp_path):
+    """include/swb200.h is a C header (the Julia ccall / cgo-style consumer sees C, not C++): it must compile as C11, and a C translation unit
+    must see the same struct sizes the library (compiled as C++ by nvcc) reports through swb_abi_layout()."""
+    import json
+    import shutil
+    import subprocess
+
+    import swb200 as S
+
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    layout = json.loads(S._lib.load().swb_abi_layout().decode())
+    src = tmp_path / "abi.c"
+    lines = ['#include "swb200.h"', "#include <stdio.h>", "int main(void) {"]
+    for name in layout:
+        lines.append(f'    printf("{name} %zu\\n", sizeof({name}));')
+    lines += ["    return 0;", "}"]
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.check_call([cc, "-std=c11", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    sizes = dict((ln.split()[0], int(ln.split()[1])) for ln in out.splitlines())
+    assert sizes == {k: v["size"] for k, v in layout.items()}
