@@ -147,3 +147,46 @@ def test_free_surface_image_source_known_answer():
     assert trapz(tt, np.abs(trace - exact)) <= np.max(np.abs(exact)) * 0.01 * (dt * nt)
     # and without the image term the criterion fails: the test discriminates
     assert trapz(tt, np.abs(trace - green(d_direct))) > np.max(np.abs(exact)) * 0.01 * (dt * nt)
+
+
+@pytest.mark.parametrize("kind,freetop", [("momten", True), ("extforce", True), ("momten", False)])
+def test_elastic_oracle_equals_independent_restatement(kind, freetop):
+    """the oracle's hand-expanded elastic C kernels (oracle/swref_elastic.h) against tests/macro_interp_elastic.py, which follows the
+    reference's wrappers function by function: tiny grid, C-PML on every side (and a free surface), off-grid sinc-spread sources and receivers,
+    Float64 -- seismograms, displacements, stresses and the eight psi arrays bit for bit"""
+    import elastic_cases as EC
+    import macro_interp_elastic as ME
+    from oracle import oracle_elastic as OE
+
+    case = EC.elastic_case(n=(27, 25), nt=40, halo=4, freetop=freetop, dtype=np.float64, kind=kind, nshots=1, nsrc=2, nrec=3, seed=71, h=5.0, f0=40.0)
+    sim = O.build_wavesim("elastic_iso", EC.params_oracle(case))
+    shot = EC.oracle_shots(case)[0]
+    sim.set_matprop(*EC.matprops(case))
+    sim.init_shot(shot)
+    sim.forward_1shot(shot)
+    lists, tf = sim.possrcrec_scaletf(shot)
+    momtens, k2 = sim._momtens(shot)
+    assert k2 == kind
+    nx, nz = case["n"]
+    h = case["halo"]
+    z = lambda *s: np.zeros(s)
+    st = dict(sxx=z(nx, nz), szz=z(nx, nz), sxz=z(nx - 1, nz - 1), uxo=z(nx - 1, nz), uzo=z(nx, nz - 1), uxc=z(nx - 1, nz), uzc=z(nx, nz - 1),
+              lam=sim.f["lam"][0], mu=sim.f["mu"][0], mu_hh=sim.f["mu_hh"][0], rho_ih=sim.f["rho_ihalf"][0], rho_jh=sim.f["rho_jhalf"][0],
+              psi_dsxxdx=z(2 * h, nz), psi_dsxzdx=z(2 * (h + 1), nz - 1), psi_dszzdz=z(nx, 2 * h), psi_dsxzdz=z(nx - 1, 2 * (h + 1)),
+              psi_duxdx=z(2 * (h + 1), nz), psi_duzdx=z(2 * h, nz - 1), psi_duxdz=z(nx - 1, 2 * h), psi_duzdz=z(nx, 2 * (h + 1)),
+              halo=h, freetop=freetop, dx=float(sim.spacing[0]), dz=float(sim.spacing[1]), dt=float(sim.dt))
+    cp = [(c.a, c.a_h, c.b, c.b_h) for c in sim.cpml]
+    traces = np.zeros((case["nt"], 2, 3))
+    for it in range(1, case["nt"] + 1):
+        ME.forward_step(st, cp, lists, tf, momtens, traces, it, kind)
+    ref = shot.seismograms
+    assert np.all(np.max(np.abs(ref), axis=0) > 0)
+    assert np.array_equal(traces, ref), float(np.max(np.abs(traces - ref)) / np.max(np.abs(ref)))
+    assert np.array_equal(st["uxc"], sim.f["ucur"][0]) and np.array_equal(st["uzc"], sim.f["ucur"][1])
+    for a, b in zip((st["sxx"], st["szz"], st["sxz"]), sim.f["sigma"]):
+        assert np.array_equal(a, b)
+    names = [("psi_dsdx", ("psi_dsxxdx", "psi_dsxzdx")), ("psi_dsdz", ("psi_dszzdz", "psi_dsxzdz")), ("psi_dudx", ("psi_duxdx", "psi_duzdx")),
+             ("psi_dudz", ("psi_duxdz", "psi_duzdz"))]
+    for oname, (n0, n1) in names:
+        assert np.array_equal(st[n0], sim.f[oname][0]) and np.array_equal(st[n1], sim.f[oname][1]), oname
+        assert np.max(np.abs(st[n0])) > 0 or np.max(np.abs(st[n1])) > 0
