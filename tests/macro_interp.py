@@ -179,3 +179,41 @@ def cd_forward_step(st, cp, possrcs, tf, posrecs, traces, it):
     for r in range(posrecs.shape[0]):
         traces[it - 1, r] = pnew[(int(posrecs[r, 0]), int(posrecs[r, 1]))]
     st["pold"], st["pcur"] = st["pcur"], st["pold"]
+
+
+# ---- acoustic3D_xPU.jl ----------------------------------------------------------------------------------------------------
+def cd3_forward_step(st, cp, possrcs, tf, posrecs, traces, it):
+    """forward_onestep_CPML! (acoustic3D_xPU.jl:96-160): st: pold, pcur (pnew aliases pold), fact, psi[3], xi[3]; rotates the handles"""
+    nx, ny, nz = st["pcur"].shape
+    n = (nx, ny, nz)
+    pold, pcur = A1(st["pold"]), A1(st["pcur"])
+    halo = st["halo"]
+    inv = [1.0 / st["d"][k] for k in range(3)]
+    psi = [A1(a) for a in st["psi"]]
+    xi = [A1(a) for a in st["xi"]]
+    for ax in range(3):  # update_ψ_x! / _y! / _z! over the 2 halo compact indices of their axis
+        (a, ah, b, bh) = cp[ax]
+        rng = [range(1, n[q] + 1) for q in range(3)]
+        rng[ax] = range(1, 2 * halo + 1)
+        for k in rng[2]:
+            for j in rng[1]:
+                for i in rng[0]:
+                    I = [i, j, k]
+                    c = I[ax]
+                    I[ax] = n[ax] - halo - 1 + (c - halo) if c > halo else c
+                    dtilde(pcur, ah, bh, psi[ax], ax + 1, tuple(I), inv[ax], halo, True, 2)
+    pnew = pold
+    for k in range(2, nz):
+        for j in range(2, ny):
+            for i in range(2, nx):
+                I = (i, j, k)
+                lap = dtilde2(pcur, cp[0][0], cp[0][2], psi[0], xi[0], 1, I, inv[0], halo)
+                lap = lap + dtilde2(pcur, cp[1][0], cp[1][2], psi[1], xi[1], 2, I, inv[1], halo)
+                lap = lap + dtilde2(pcur, cp[2][0], cp[2][2], psi[2], xi[2], 3, I, inv[2], halo)
+                pnew[I] = 2.0 * pcur[I] - pold[I] + st["fact"][i - 1, j - 1, k - 1] * lap
+    for s in range(possrcs.shape[0]):
+        q = tuple(int(v) for v in possrcs[s, :])
+        pnew[q] = pnew[q] + tf[it - 1, s]
+    for r in range(posrecs.shape[0]):
+        traces[it - 1, r] = pnew[tuple(int(v) for v in posrecs[r, :])]
+    st["pold"], st["pcur"] = st["pcur"], st["pold"]

@@ -190,3 +190,29 @@ def test_elastic_oracle_equals_independent_restatement(kind, freetop):
     for oname, (n0, n1) in names:
         assert np.array_equal(st[n0], sim.f[oname][0]) and np.array_equal(st[n1], sim.f[oname][1]), oname
         assert np.max(np.abs(st[n0])) > 0 or np.max(np.abs(st[n1])) > 0
+
+
+@pytest.mark.parametrize("freetop", [False, True])
+def test_cd3d_oracle_equals_generator_interpreter(freetop):
+    case = cases.acoustic_case(kind="acoustic_cd", n=(13, 12, 14), nt=24, halo=3, freetop=freetop, dtype=np.float64, nshots=1, nsrc=2, nrec=4, seed=53, f0=40.0)
+    sh = case["shots"][0]
+    ext = [(case["n"][d] - 1) * case["h"] for d in range(3)]
+    sh["rec_positions"][0] = [0.1 * ext[0], 0.5 * ext[1], 0.5 * ext[2]]   # receivers inside the C-PML strips too
+    sh["rec_positions"][1] = [0.5 * ext[0], 0.92 * ext[1], 0.9 * ext[2]]
+    sim = O.build_wavesim("acoustic_cd", cases.case_params_oracle(case))
+    shot = cases.oracle_shots(case)[0]
+    sim.set_matprop(case["vp"])
+    sim.init_shot(shot)
+    sim.forward_1shot(shot)
+    possrcs, posrecs, tf = sim.possrcrec_scaletf(shot)
+    n, h = case["n"], case["halo"]
+    shp = lambda ax, w: tuple(w if q == ax else n[q] for q in range(3))
+    st = dict(pold=np.zeros(n), pcur=np.zeros(n), fact=sim.f["fact"][0], psi=[np.zeros(shp(ax, 2 * h)) for ax in range(3)],
+              xi=[np.zeros(shp(ax, 2 * (h + 1))) for ax in range(3)], halo=h, d=[float(s) for s in sim.spacing])
+    cp = [(c.a, c.a_h, c.b, c.b_h) for c in sim.cpml]
+    traces = np.zeros((case["nt"], posrecs.shape[0]))
+    for it in range(1, case["nt"] + 1):
+        MI.cd3_forward_step(st, cp, possrcs, tf, posrecs, traces, it)
+    assert np.all(np.max(np.abs(traces), axis=0) > 0)
+    assert np.array_equal(traces, shot.seismograms)
+    assert np.max(np.abs(st["psi"][2])) > 0 and np.max(np.abs(st["xi"][1])) > 0
