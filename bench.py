@@ -382,8 +382,8 @@ class C2Bench:
         full = self.args.grid == 4096
         roof = {"bound": "hbm", "kernel": "vd_fused_kernel<float,%s,0,16> (v update + p update + inject + record, one launch per time step)" % ("float" if fast else "double"),
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": 583.2e6 if (full and fast) else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one forward launch, ncu --set full (profiles/r1_ncu_vd_fwd_v6.txt)",
+                "traffic": 582.0e6 if (full and fast) else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one forward launch, ncu --set full, cold caches (profiles/r2_ncu_vd_fwd.txt)",
                 "peak_source": peak_src, "frac_of_8TBs_nominal": ach / 8000.0, "avg_launch_us": dur * 1e6, "timed_launches": kt_n,
                 "algorithmic_bytes_per_launch": 36 * n * n,
                 "sampling": "CUDA events on the engine's stream around each forward-sweep graph (nt step launches + the checkpoint "
@@ -392,7 +392,8 @@ class C2Bench:
             dur_a = (ka_ms - kr_n * (kt_ms / kt_n)) / ka_n * 1e-3
             ach_a = 68 * n * n / dur_a / 1e9
             roof["adjoint_kernel"] = {"achieved": ach_a, "frac": ach_a / peak, "avg_launch_us": dur_a * 1e6, "timed_launches": ka_n,
-                                      "algorithmic_bytes_per_launch": 68 * n * n}
+                                      "algorithmic_bytes_per_launch": 68 * n * n, "traffic": 1112.5e6 if (full and fast) else None,
+                                      "traffic_source": "profiles/r2_ncu_vd_adj.txt"}
         return roof
 
     def e2e(self, ws, nshots):
