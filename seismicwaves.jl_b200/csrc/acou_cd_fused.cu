@@ -500,6 +500,447 @@ __global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? CDF_RIM_MINB : CD
     cd_rim_body<T, CT, HAS_Y, ADJ, FMA>(P, (int)blockIdx.x, (int)threadIdx.x);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// rim kernel, z-marching form (3D)
+// ---------------------------------------------------------------------------------------------------------------------
+// The per-vector rim kernel above re-fetches three planes of pcur per cell and spends ~650 warp instructions per vector, more than
+// half of them address arithmetic (ncu, 768^3: 3.9 TB/s on its own traffic, issue slots 43 % busy at 42 % occupancy).  Here a thread
+// owns one (x-vector, row) column of a rim box and marches it along z like a bulk thread: pcur[k-1], pcur[k], pcur[k+1] in a
+// register queue, and everything plane k + 1 needs -- pcur[k+2], pold, fact, the y neighbours and the memory variables of the
+// box's own strip axis -- is requested before the arithmetic of plane k.  Everything that does not change along the march is hoisted:
+// "this row is a y face" is a property of the thread, the C-PML coefficients come from per-CTA shared-memory tables (x strips: one
+// record per strip vector; z strips: one record per strip index) or registers (y strip: one strip index per row), addresses advance
+// by running offsets, the two prefetch buffers swap roles in a loop unrolled by two, and the last iteration re-requests its own plane
+// instead of predicating every prefetch.  The V + 1 staggered derivatives / psi values of an x-strip vector are computed once each
+// (psi_lo of cell v + 1 is psi_hi of cell v: same operands), and along a z strip psi_lo of plane k + 1 is the psi_hi plane k just
+// computed.  Strips of the other axes that cross a box (edges and corners of the grid) fetch their memory variables on demand.
+// Values are those of cd_rim_body operation for operation.
+
+// one cell, one axis of @∇̃² with preloaded memory variables (same operations as cd_axis_term / cd_axis_term_vec);
+// lo_given: psi_lo already holds the new value (computed by the previous plane of a z march)
+template <class T, class CT>
+__device__ __forceinline__ CT cd_axis_cell(const CT (&w1)[2], CT D2, CT lo, CT mid, CT hi, T inv, T ah1, T bh1, T ah0, T bh0, T a1, T b1, T ph, T pl, T xo,
+                                           T &psi_hi, T &psi_lo, T &xn, bool lo_given = false)
+{
+    const CT Dhi = (w1[0] * mid + w1[1] * hi) * (CT)inv;
+    (void)cpml_apply<T, CT>(Dhi, ah1, bh1, ph, psi_hi);
+    if (!lo_given) {
+        const CT Dlo = (w1[0] * lo + w1[1] * mid) * (CT)inv;
+        (void)cpml_apply<T, CT>(Dlo, ah0, bh0, pl, psi_lo);
+    }
+    const CT dpsi = (w1[0] * (CT)psi_lo + w1[1] * (CT)psi_hi) * (CT)inv;
+    const T bx = b1 * xo;
+    xn = (T)((CT)bx + (CT)a1 * (D2 + dpsi));
+    return (D2 + dpsi) + (CT)xn;
+}
+
+// x-strip description of the vector starting at cell i0: first strip index s0 (cell v has index s0 + v), mask of updated strip cells,
+// mask of cells that also own the strip's first psi entry
+template <int V>
+__device__ __forceinline__ void cd_xstrip_desc(int i0, int nx, int h, int &s0, int &xm, int &xfirst)
+{
+    s0 = 0, xm = 0, xfirst = 0;
+    if (h <= 0 || !(i0 + 1 <= h || i0 + V >= nx - h + 1))
+        return;
+    const bool lo_side = i0 + 1 <= h; // (the host guarantees nx >= 2 h + V: a vector never touches both strips)
+    s0 = lo_side ? i0 + 1 : i0 + 1 - (nx - h) + 1 + h;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int c1b = i0 + v + 1;
+        const bool in = lo_side ? c1b <= h : c1b >= nx - h + 1;
+        if (in && c1b >= 2 && c1b <= nx - 1) {
+            xm |= 1 << v;
+            if (c1b == 2 || c1b == nx - h + 1)
+                xfirst |= 1 << v;
+        }
+    }
+}
+// psi entries s0 - 2 + e, e = 0 .. V, needed by the updated cells
+template <int V>
+__device__ __forceinline__ int cd_xstrip_need(int xm)
+{
+    return (xm | (xm << 1)) & ((1 << (V + 1)) - 1);
+}
+// per-CTA tables in shared memory.  x: record r (5 V values) of x-strip vector r: a_h[e], e < V | b_h[e], e < V | a[v] | b[v] | a_h[V], b_h[V];
+// z: record s (8 values) of strip index s: a_h[s-1], b_h[s-1], a_h[s-2], b_h[s-2], a[s-1], b[s-1]
+template <class T, int V>
+__device__ __forceinline__ int cd_xtab_records(const CdFusedParams<T> &P)
+{
+    return P.ivlo + ((int)(P.ld / V) - P.ivhi);
+}
+template <class T, int V>
+__device__ __forceinline__ void cd_rimz_tables(const CdFusedParams<T> &P, T *xtab, T *ztab, bool with_z, int tid, int nthreads)
+{
+    const int nrec = cd_xtab_records<T, V>(P);
+    for (int r = tid; r < nrec; r += nthreads) {
+        const int iv = r < P.ivlo ? r : P.ivhi + (r - P.ivlo);
+        int s0, xm, xf;
+        cd_xstrip_desc<V>(iv * V, P.nx, P.halo, s0, xm, xf);
+        const int need = cd_xstrip_need<V>(xm);
+        T *q = xtab + r * (5 * V);
+#pragma unroll
+        for (int e = 0; e <= V; ++e) {
+            const bool on = (need >> e) & 1;
+            const T ah = on ? P.a_h[0][s0 - 2 + e] : (T)0, bh = on ? P.b_h[0][s0 - 2 + e] : (T)0;
+            q[e < V ? e : 4 * V] = ah;
+            q[e < V ? V + e : 4 * V + 1] = bh;
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const bool on = (xm >> v) & 1;
+            q[2 * V + v] = on ? P.a[0][s0 - 1 + v] : (T)0;
+            q[3 * V + v] = on ? P.b[0][s0 - 1 + v] : (T)0;
+        }
+    }
+    if (with_z)
+        for (int s = 2 + tid; s <= 2 * P.halo; s += nthreads) {
+            T *q = ztab + s * 8;
+            q[0] = P.a_h[2][s - 1], q[1] = P.b_h[2][s - 1], q[2] = P.a_h[2][s - 2], q[3] = P.b_h[2][s - 2], q[4] = P.a[2][s - 1], q[5] = P.b[2][s - 1];
+        }
+}
+
+// x term of @∇̃² for the V cells of a strip vector.  psv[e] = psi_in[s0 - 2 + e], xiv[v] = xi[s0 - 1 + v] (already loaded);
+// ps_out -> psi_out[s0 - 2], xs -> xi[s0 - 1] of this (row, plane).  Same operations per cell as cd_axis_term.
+template <class T, class CT, int V, bool FMA>
+__device__ __forceinline__ void cd_xstrip_vec(CT (&lap)[V], const CT (&w1)[2], const CT (&w2)[3], const CVec<T, V> &qc, T xl_in, T xr_in, T inv, int xm, int xfirst,
+                                              const T *rec, const T (&psv)[V + 1], const T (&xiv)[V], T *__restrict__ ps_out, T *__restrict__ xs)
+{
+    typedef CVec<T, V> VT;
+    const VT ah = *reinterpret_cast<const VT *>(rec), bh = *reinterpret_cast<const VT *>(rec + V);
+    const VT a = *reinterpret_cast<const VT *>(rec + 2 * V), b = *reinterpret_cast<const VT *>(rec + 3 * V);
+    const T ahV = rec[4 * V], bhV = rec[4 * V + 1];
+    CT p[V + 2];
+    p[0] = (CT)xl_in;
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        p[v + 1] = (CT)qc.v[v];
+    p[V + 1] = (CT)xr_in;
+    T psn[V + 1];
+#pragma unroll
+    for (int e = 0; e <= V; ++e) { // staggered derivative between cells e - 1 and e of the vector, and its memory variable
+        const CT D = (w1[0] * p[e] + w1[1] * p[e + 1]) * (CT)inv;
+        (void)cpml_apply<T, CT>(D, e < V ? ah.v[e < V ? e : 0] : ahV, e < V ? bh.v[e < V ? e : 0] : bhV, psv[e], psn[e]);
+    }
+    const CT inv2 = (CT)(inv * inv);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const CT D2 = d2<CT, FMA>(w2, p[v], p[v + 1], p[v + 2], inv2);
+        if ((xm >> v) & 1) {
+            const CT dpsi = (w1[0] * (CT)psn[v] + w1[1] * (CT)psn[v + 1]) * (CT)inv;
+            const T bx = b.v[v] * xiv[v];
+            const T xn = (T)((CT)bx + (CT)a.v[v] * (D2 + dpsi));
+            lap[v] = (D2 + dpsi) + (CT)xn;
+            ps_out[v + 1] = psn[v + 1];
+            if ((xfirst >> v) & 1) // the strip's first entry has no interior cell of its own
+                ps_out[v] = psn[v];
+            xs[v] = xn;
+        } else
+            lap[v] = D2;
+    }
+}
+
+#ifndef CDF_RIMZ_MINB
+// 3 CTAs of 168 registers per SM.  Measured on 768^3 (rim launch alone): 4 CTAs / 128 registers the same 0.53-0.54 ms; single-buffered loads
+// behind an L2 prefetch two planes ahead at 4 / 5 / 6 CTAs per SM 0.57 / 0.66 / 0.78 ms (spills): more warps do not pay here
+#define CDF_RIMZ_MINB 3
+#endif
+template <class T, int V>
+struct RimPre { // what a march thread requests one plane ahead
+    CVec<T, V> po, fc, yu, yd; // pold, fact, pcur of rows j - 1 and j + 1
+    T xl, xr;                  // pcur of the cells left and right of the vector
+    CVec<T, V> ph, pl, xo;     // own strip axis y / z: psi[s - 1], psi[s - 2] (y only), xi[s - 1]
+    T psv[V + 1], xiv[V];      // own strip axis x: psi_x[s0 - 2 ..], xi_x[s0 - 1 ..]
+};
+
+template <class T, class CT, int KIND, bool ADJ, bool FMA>
+__device__ __forceinline__ void cd_rimz_body(const CdFusedParams<T> &P, const CdBox &B, const CdRimTile &R, const int local, const int cta, const int tid,
+                                             const T *xtab, const T *ztab)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    typedef CVec<T, V> VT;
+    typedef RimPre<T, V> Pre;
+    const int li = tid % R.tw, lj = tid / R.tw;
+    const int tx_ = local % R.ntx, r_ = local / R.ntx, ty_ = r_ % R.nty, tz_ = r_ / R.nty;
+    const int ivl = tx_ * R.tw + li, jl = ty_ * R.th + lj;
+    if (lj >= R.th || ivl >= B.nvx || jl >= B.ny)
+        return; // no barriers below, no shuffles: threads leave freely
+    const int iv = B.iv0 + ivl, j = B.j0 + jl, i0 = iv * V;
+    const int k0 = B.k0 + tz_ * R.zc, k1 = min(k0 + R.zc, B.k0 + B.nz); // KIND 0 / 1: interior planes only, 1 <= k <= nz - 2
+    const int nx = P.nx, ny = P.ny, nz = P.nz, h = P.halo;
+    const long long ld = P.ld, plane = P.plane;
+    const bool has_inj = P.inj_it > 0 && P.inj[1].off[cta + 1] > P.inj[1].off[cta];
+    const bool has_rec = P.rec_it > 0 && P.rec[1].off[cta + 1] > P.rec[1].off[cta];
+    int okm = 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        if (i0 + v >= 1 && i0 + v <= nx - 2)
+            okm |= 1 << v;
+    const long long col = (long long)j * ld + i0;
+    long long off = (long long)k0 * plane + col;
+
+    auto finish = [&](int k, long long o, VT out, const VT &c2, const VT &c1, const VT &c0, VT g) {
+        const int code0 = ((k - k0) * CDF_RIM_T + tid) * V;
+        if (has_inj)
+            inject_points<T, V>(P, P.inj[1], cta, code0, out);
+        stv<T, V>(P.pnew + o, out);
+        if (P.peer_lo != nullptr && k == 1) // boundary planes of a z slab go straight into the neighbour's ghost plane (NVLink peer store)
+            stv<T, V>(P.peer_lo + (o - plane), out);
+        if (P.peer_hi != nullptr && k == nz - 2)
+            stv<T, V>(P.peer_hi + (o - (long long)(nz - 2) * plane), out);
+        if (has_rec)
+            record_points<T, V>(P, P.rec[1], cta, code0, out);
+        if (ADJ) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                g.v[v] = correlate<T, CT, FMA>(g.v[v], out.v[v], c2.v[v], c1.v[v], c0.v[v], P.inv_dt2);
+            stv<T, V>(P.grad + o, g);
+        }
+    };
+    auto copy_plane = [&](int k, long long o) { // a face cell is never updated (pnew aliases pold in the reference)
+        if (KIND == 2 && ((k == 0 && P.ghost_lo) || (k == nz - 1 && P.ghost_hi)))
+            return; // ghost plane of a z slab: written by the neighbour that owns it
+        VT c2 = {}, c1 = {}, c0 = {}, g = {};
+        if (ADJ) {
+            c2 = ldv<T, V>(P.pm2 + o);
+            c1 = ldv<T, V>(P.pm1 + o);
+            c0 = ldv<T, V>(P.p0 + o);
+            g = ldv<T, V>(P.grad + o);
+        }
+        finish(k, o, ldv<T, V>(P.pold + o), c2, c1, c0, g);
+    };
+
+    if (KIND != 0 && !(j >= 1 && j <= ny - 2)) { // a y face row
+#pragma unroll 1
+        for (int k = k0; k < k1; ++k, off += plane)
+            copy_plane(k, off);
+        return;
+    }
+
+    const CT w1[2] = {(CT)P.c1[0], (CT)P.c1[1]};
+    const CT w2[3] = {(CT)P.c2[0], (CT)P.c2[1], (CT)P.c2[2]};
+    const CT i2x = (CT)(P.inv_d[0] * P.inv_d[0]), i2y = (CT)(P.inv_d[1] * P.inv_d[1]), i2z = (CT)(P.inv_d[2] * P.inv_d[2]);
+    // x strip of this vector (KIND 0: the box itself; KIND 1 / 2: the columns where the box crosses the x strips)
+    int s0, xm, xfirst;
+    cd_xstrip_desc<V>(i0, nx, h, s0, xm, xfirst);
+    const int xneed = cd_xstrip_need<V>(xm);
+    const T *xrec = xtab + (iv < P.ivlo ? iv : P.ivlo + (iv - P.ivhi)) * (5 * V);
+    const long long xpinc = (long long)ny * (2 * h), xxinc = (long long)ny * (2 * (h + 1));
+    long long xpo = ((long long)k0 * ny + j) * (2 * h) + (s0 - 2), xxo = ((long long)k0 * ny + j) * (2 * (h + 1)) + (s0 - 1);
+    // y strip of this row (KIND 1: the box itself; KIND 2: the rows where the z planes cross the y strips)
+    const int sy = (KIND != 0 && h > 0) ? strip_index(j + 1, ny, h) : 0;
+    T yah1 = (T)0, ybh1 = (T)0, yah0 = (T)0, ybh0 = (T)0, ya1 = (T)0, yb1 = (T)0;
+    if (KIND != 0 && sy > 0)
+        yah1 = P.a_h[1][sy - 1], ybh1 = P.b_h[1][sy - 1], yah0 = P.a_h[1][sy - 2], ybh0 = P.b_h[1][sy - 2], ya1 = P.a[1][sy - 1], yb1 = P.b[1][sy - 1];
+    const bool ylo_store = j + 1 == 2 || j + 1 == ny - h + 1;
+    const long long ypinc = ld * (2 * h), yxinc = ld * (2 * (h + 1));
+    long long ypo = (long long)k0 * ypinc + i0 + (long long)(sy - 2) * ld, yxo_ = (long long)k0 * yxinc + i0 + (long long)(sy - 1) * ld;
+    // z strip (KIND 2): active strip index of plane k (0: plain or face)
+    const long long zst = ld * ny;
+    auto z_index = [&](int k) -> int {
+        if (KIND != 2 || h <= 0 || k < 1 || k > nz - 2)
+            return 0;
+        const int sz = strip_index(k + 1, nz, h);
+        return (sz > 0 && (sz <= h ? P.zpml_lo != 0 : P.zpml_hi != 0)) ? sz : 0;
+    };
+
+    // requests of plane kn (always a valid plane; KIND 2: possibly a face)
+    auto load_pre = [&](Pre &q, int kn, long long o, long long xp, long long xx, long long yp, long long yx) {
+        q.po = ldv<T, V>(P.pold + o);
+        q.fc = ldv<T, V>(P.fact + o);
+        q.yu = ldv<T, V>(P.pcur + o - ld);
+        q.yd = ldv<T, V>(P.pcur + o + ld);
+        if (i0 > 0)
+            q.xl = P.pcur[o - 1];
+        if (i0 + V < nx)
+            q.xr = P.pcur[o + V];
+        if (KIND == 0) {
+            const T *ps = P.psi_in[0] + xp, *xs = P.xi[0] + xx;
+#pragma unroll
+            for (int e = 0; e <= V; ++e)
+                if ((xneed >> e) & 1)
+                    q.psv[e] = ps[e];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if ((xm >> v) & 1)
+                    q.xiv[v] = xs[v];
+        }
+        if (KIND == 1 && sy > 0) {
+            q.pl = ldv<T, V>(P.psi_in[1] + yp);
+            q.ph = ldv<T, V>(P.psi_in[1] + yp + ld);
+            q.xo = ldv<T, V>(P.xi[1] + yx);
+        }
+        if (KIND == 2) {
+            const int sz = z_index(kn);
+            if (sz > 0) {
+                q.ph = ldv<T, V>(P.psi_in[2] + col + (long long)(sz - 1) * zst);
+                q.xo = ldv<T, V>(P.xi[2] + col + (long long)(sz - 1) * zst);
+            }
+        }
+    };
+
+    // queue: rows j +- 1 exist (y faces left above), planes are clamped into the grid (a clamped value is only seen by a face plane)
+    VT qm = ldv<T, V>(P.pcur + off - (k0 >= 1 ? plane : 0)), qc = ldv<T, V>(P.pcur + off), qp = ldv<T, V>(P.pcur + off + (k0 + 1 <= nz - 1 ? plane : 0));
+    Pre A = {}, Bf = {};
+    load_pre(A, k0, off, xpo, xxo, ypo, yxo_);
+    VT zcarry = {};     // KIND 2: the new psi_z[s - 1] of the previous plane = psi_lo of this one
+    bool zhave = false;
+
+    auto iter = [&](const int k, Pre &cur, Pre &nxt) {
+        const bool more = k + 1 < k1; // the last plane re-requests itself (cache hits) instead of predicating every prefetch
+        const long long dn = more ? plane : 0;
+        const bool zface = KIND == 2 && (k < 1 || k > nz - 2);
+        const int sz = z_index(k);
+        // L1TEX returns a warp's loads in order: what this plane still has to fetch itself goes out before the prefetch of the next one
+        VT c2 = {}, c1 = {}, c0 = {}, g = {};
+        if (ADJ && !zface) {
+            c2 = ldv<T, V>(P.pm2 + off);
+            c1 = ldv<T, V>(P.pm1 + off);
+            c0 = ldv<T, V>(P.p0 + off);
+            g = ldv<T, V>(P.grad + off);
+        }
+        T cpsv[V + 1], cxiv[V]; // the box crosses an x strip here (KIND 1 / 2): memory variables on demand
+        if (KIND != 0 && xm != 0 && !zface) {
+            const T *ps = P.psi_in[0] + xpo, *xs = P.xi[0] + xxo;
+#pragma unroll
+            for (int e = 0; e <= V; ++e)
+                cpsv[e] = ((xneed >> e) & 1) ? ps[e] : (T)0;
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                cxiv[v] = ((xm >> v) & 1) ? xs[v] : (T)0;
+        }
+        VT yph = cur.ph, ypl = cur.pl, yxo = cur.xo, zpl = zcarry;
+        if (KIND == 2 && !zface) {
+            if (sy > 0) { // z planes crossing a y strip
+                ypl = ldv<T, V>(P.psi_in[1] + ypo);
+                yph = ldv<T, V>(P.psi_in[1] + ypo + ld);
+                yxo = ldv<T, V>(P.xi[1] + yxo_);
+            }
+            if (sz > 0 && !zhave) // first strip plane of this march
+                zpl = ldv<T, V>(P.psi_in[2] + col + (long long)(sz - 2) * zst);
+        }
+        const VT qn = ldv<T, V>(P.pcur + off + dn + ((KIND != 2 || k + (more ? 2 : 1) <= nz - 1) ? plane : 0));
+        load_pre(nxt, more ? k + 1 : k, off + dn, xpo + (more ? xpinc : 0), xxo + (more ? xxinc : 0), ypo + (more ? ypinc : 0), yxo_ + (more ? yxinc : 0));
+        if (zface) {
+            copy_plane(k, off);
+            zhave = false;
+        } else {
+            const T xl_in = cur.xl, xr_in = cur.xr;
+            CT pc[V], lap[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                pc[v] = (CT)qc.v[v];
+            // ---- x term ------------------------------------------------------------------------------------------------
+            if (KIND == 0)
+                cd_xstrip_vec<T, CT, V, FMA>(lap, w1, w2, qc, xl_in, xr_in, P.inv_d[0], xm, xfirst, xrec, cur.psv, cur.xiv, P.psi_out[0] + xpo, P.xi[0] + xxo);
+            else if (xm != 0)
+                cd_xstrip_vec<T, CT, V, FMA>(lap, w1, w2, qc, xl_in, xr_in, P.inv_d[0], xm, xfirst, xrec, cpsv, cxiv, P.psi_out[0] + xpo, P.xi[0] + xxo);
+            else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const CT xl = (CT)(v > 0 ? qc.v[v > 0 ? v - 1 : 0] : xl_in);
+                    const CT xr = (CT)(v < V - 1 ? qc.v[v < V - 1 ? v + 1 : 0] : xr_in);
+                    lap[v] = d2<CT, FMA>(w2, xl, pc[v], xr, i2x);
+                }
+            }
+            // ---- y term ------------------------------------------------------------------------------------------------
+            if (KIND != 0 && sy > 0) {
+                const VT ph = yph, pl = ypl, xo = yxo;
+                VT psi_hi = ph, psi_lo = pl, xn = xo;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    CT t = d2<CT, FMA>(w2, (CT)cur.yu.v[v], pc[v], (CT)cur.yd.v[v], i2y);
+                    if ((okm >> v) & 1)
+                        t = cd_axis_cell<T, CT>(w1, t, (CT)cur.yu.v[v], pc[v], (CT)cur.yd.v[v], P.inv_d[1], yah1, ybh1, yah0, ybh0, ya1, yb1, ph.v[v], pl.v[v], xo.v[v],
+                                                psi_hi.v[v], psi_lo.v[v], xn.v[v]);
+                    lap[v] = lap[v] + t;
+                }
+                stv<T, V>(P.psi_out[1] + ypo + ld, psi_hi);
+                if (ylo_store)
+                    stv<T, V>(P.psi_out[1] + ypo, psi_lo);
+                stv<T, V>(P.xi[1] + yxo_, xn);
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    lap[v] = lap[v] + d2<CT, FMA>(w2, (CT)cur.yu.v[v], pc[v], (CT)cur.yd.v[v], i2y);
+            }
+            // ---- z term, leapfrog ----------------------------------------------------------------------------------------
+            CT t[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                t[v] = d2<CT, FMA>(w2, (CT)qm.v[v], pc[v], (CT)qp.v[v], i2z);
+            if (KIND == 2 && sz > 0) {
+                const VT za = *reinterpret_cast<const VT *>(ztab + sz * 8);                 // a_h[s-1], b_h[s-1], a_h[s-2], b_h[s-2] (Float64: the first two)
+                const VT zb = *reinterpret_cast<const VT *>(ztab + sz * 8 + V);             // Float32: a[s-1], b[s-1]; Float64: a_h[s-2], b_h[s-2]
+                const T ah1 = za.v[0], bh1 = za.v[1];
+                const T ah0 = V == 4 ? za.v[V == 4 ? 2 : 0] : zb.v[0], bh0 = V == 4 ? za.v[V == 4 ? 3 : 0] : zb.v[1];
+                const T a1 = ztab[sz * 8 + 4], b1 = ztab[sz * 8 + 5];
+                const VT pl = zpl;
+                VT psi_hi = cur.ph, psi_lo = pl, xn = cur.xo;
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if ((okm >> v) & 1)
+                        t[v] = cd_axis_cell<T, CT>(w1, t[v], (CT)qm.v[v], pc[v], (CT)qp.v[v], P.inv_d[2], ah1, bh1, ah0, bh0, a1, b1, cur.ph.v[v], pl.v[v],
+                                                   cur.xo.v[v], psi_hi.v[v], psi_lo.v[v], xn.v[v], zhave);
+                stv<T, V>(P.psi_out[2] + col + (long long)(sz - 1) * zst, psi_hi);
+                if (k + 1 == 2 || k + 1 == nz - h + 1)
+                    stv<T, V>(P.psi_out[2] + col + (long long)(sz - 2) * zst, psi_lo);
+                stv<T, V>(P.xi[2] + col + (long long)(sz - 1) * zst, xn);
+                zcarry = psi_hi;
+                zhave = true;
+            } else if (KIND == 2)
+                zhave = false;
+            VT out = cur.po;
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if ((okm >> v) & 1)
+                    out.v[v] = leapfrog<T, CT, FMA>(pc[v], cur.po.v[v], cur.fc.v[v], lap[v] + t[v]);
+            finish(k, off, out, c2, c1, c0, g);
+        }
+        qm = qc;
+        qc = qp;
+        qp = qn;
+        off += plane;
+        xpo += xpinc, xxo += xxinc;
+        ypo += ypinc, yxo_ += yxinc;
+    };
+    int k = k0;
+#pragma unroll 1
+    for (; k + 1 < k1; k += 2) {
+        iter(k, A, Bf);
+        iter(k + 1, Bf, A);
+    }
+    if (k < k1)
+        iter(k, A, Bf);
+}
+
+template <class T, class CT, bool ADJ, bool FMA>
+__global__ void __launch_bounds__(CDF_RIM_T, CDF_RIMZ_MINB) cd_rimz_kernel(const CdFusedParams<T> P)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    const int cta = (int)blockIdx.x;
+    int bi = 0;
+#pragma unroll
+    for (int b = 1; b < CDF_MAX_BOX; ++b)
+        if (b < P.nbox && cta >= P.rt[b].cta0)
+            bi = b;
+    const CdBox &B = P.box[bi];
+    const CdRimTile &R = P.rt[bi];
+    const int local = cta - R.cta0;
+    if ((P.rim_skip >> R.kind) & 1)
+        return;
+    extern __shared__ __align__(16) unsigned char cdf_smem[];
+    T *xtab = reinterpret_cast<T *>(cdf_smem);
+    T *ztab = xtab + (cd_xtab_records<T, V>(P) * 5 * V + 7) / 8 * 8;
+    cd_rimz_tables<T, V>(P, xtab, ztab, R.kind == 2, (int)threadIdx.x, CDF_RIM_T);
+    __syncthreads();
+    if (R.kind == 0)
+        cd_rimz_body<T, CT, 0, ADJ, FMA>(P, B, R, local, cta, (int)threadIdx.x, xtab, ztab);
+    else if (R.kind == 1)
+        cd_rimz_body<T, CT, 1, ADJ, FMA>(P, B, R, local, cta, (int)threadIdx.x, xtab, ztab);
+    else
+        cd_rimz_body<T, CT, 2, ADJ, FMA>(P, B, R, local, cta, (int)threadIdx.x, xtab, ztab);
+}
+
 // Small 2D grids: both CTA kinds in one launch (the 2D bulk CTA and the rim CTA have 128 threads each).  A step of a grid that
 // fills the GPU for a few microseconds is bound by launch and fork / join latency, not by bandwidth: one kernel node per step
 // instead of two parallel ones plus the join.
@@ -519,7 +960,7 @@ __global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? 8 : 4) cd_merged2
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
-CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool has_y, int zc, bool zpml_lo, bool zpml_hi)
+CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool has_y, int zc, bool zpml_lo, bool zpml_hi, int rim_zc)
 {
     CdFusedGeom g{};
     g.v = cdf_vec(esize);
@@ -547,25 +988,41 @@ CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool h
         g.gx = g.gy = g.gz = 0;
     // rim boxes: z slabs, then y slabs between them, then x slabs inside both
     long long start = 0;
-    auto add = [&](int iv0, int nvx, int j0, int nyb, int k0, int nzb) {
+    g.rim_zc = has_y && nx >= 2 * halo + g.v ? std::max(rim_zc, 0) : 0; // (a vector of the march never touches both x strips)
+    long long cta0 = 0;
+    auto add = [&](int iv0, int nvx, int j0, int nyb, int k0, int nzb, int kind) {
         if (nvx <= 0 || nyb <= 0 || nzb <= 0)
             return;
         SWB_REQUIRE((long long)nvx * nyb * nzb < (1ll << 31), "grid too large for the fused CD rim enumeration");
+        CdRimTile &t = g.rt[g.nbox];
         CdBox &b = g.box[g.nbox++];
         b.iv0 = iv0, b.j0 = j0, b.k0 = k0, b.nvx = nvx, b.ny = nyb, b.nz = nzb, b.start = start;
         start += (long long)nvx * nyb * nzb;
+        if (g.rim_zc > 0) { // march enumeration: tiles of columns x chunks of planes
+            t.tw = std::min(nvx, 32);
+            t.th = std::min(CDF_RIM_T / t.tw, nyb);
+            t.ntx = (nvx + t.tw - 1) / t.tw;
+            t.nty = (nyb + t.th - 1) / t.th;
+            t.zc = kind == 2 ? std::min(nzb, 32) : std::min(nzb, g.rim_zc);
+            t.ntz = (nzb + t.zc - 1) / t.zc;
+            t.kind = kind;
+            SWB_REQUIRE(cta0 + (long long)t.ntx * t.nty * t.ntz < (1ll << 31), "grid too large for the fused CD rim march");
+            t.cta0 = (int)cta0;
+            cta0 += (long long)t.ntx * t.nty * t.ntz;
+        }
     };
     const int zlo = std::min(g.klo, nz), zhi = std::max(g.khi, zlo); // planes [0, zlo) and [zhi, nz) are rim
-    add(0, nvec, 0, ny, 0, zlo);
-    add(0, nvec, 0, ny, zhi, nz - zhi);
+    add(0, nvec, 0, ny, 0, zlo, 2);
+    add(0, nvec, 0, ny, zhi, nz - zhi, 2);
     if (has_y) {
         const int ylo = std::min(g.jlo, ny), yhi = std::max(g.jhi, ylo);
-        add(0, nvec, 0, ylo, zlo, zhi - zlo);
-        add(0, nvec, yhi, ny - yhi, zlo, zhi - zlo);
+        add(0, nvec, 0, ylo, zlo, zhi - zlo, 1);
+        add(0, nvec, yhi, ny - yhi, zlo, zhi - zlo, 1);
     }
-    add(0, g.ivlo, g.jlo, g.jhi - g.jlo, zlo, zhi - zlo);
-    add(g.ivhi, nvec - g.ivhi, g.jlo, g.jhi - g.jlo, zlo, zhi - zlo);
+    add(0, g.ivlo, g.jlo, g.jhi - g.jlo, zlo, zhi - zlo, 0);
+    add(g.ivhi, nvec - g.ivhi, g.jlo, g.jhi - g.jlo, zlo, zhi - zlo, 0);
     g.nrimvec = start;
+    g.nrimz_cta = (int)cta0;
     return g;
 }
 
@@ -593,6 +1050,13 @@ int cd_fused_locate(const CdFusedGeom &g, int i, int j, int k, int *cta, int *co
     for (int b = 0; b < g.nbox; ++b) {
         const CdBox &B = g.box[b];
         if (iv >= B.iv0 && iv < B.iv0 + B.nvx && j >= B.j0 && j < B.j0 + B.ny && k >= B.k0 && k < B.k0 + B.nz) {
+            if (g.rim_zc > 0) {
+                const CdRimTile &R = g.rt[b];
+                const int ivl = iv - B.iv0, jl = j - B.j0, kl = k - B.k0;
+                *cta = R.cta0 + ((kl / R.zc) * R.nty + jl / R.th) * R.ntx + ivl / R.tw;
+                *code = ((kl % R.zc) * CDF_RIM_T + (jl % R.th) * R.tw + ivl % R.tw) * g.v + i % g.v;
+                return 1;
+            }
             const long long lin = B.start + ((long long)(k - B.k0) * B.ny + (j - B.j0)) * B.nvx + (iv - B.iv0);
             *cta = (int)(lin / CDF_RIM_T);
             *code = (int)(lin % CDF_RIM_T) * g.v + i % g.v;
@@ -611,6 +1075,8 @@ void cd_fused_fill_geom(CdFusedParams<T> &P, const CdFusedGeom &g)
     for (int b = 0; b < g.nbox; ++b)
         P.box[b] = g.box[b];
     P.nrimvec = g.nrimvec;
+    for (int b = 0; b < g.nbox; ++b)
+        P.rt[b] = g.rt[b];
 }
 
 template <class T>
@@ -620,6 +1086,9 @@ void cd_fused_launch(const CdFusedParams<T> &P, const CdFusedGeom &g, bool adj, 
     const dim3 grd(g.gx, g.gy, g.gz), blk(32, g.ty, 1);
     const unsigned nrim = (unsigned)g.ncta_rim();
     const bool f32fast = sizeof(T) == 4 && fast, has_y = g.has_y;
+    // x-strip coefficient table of the marching rim kernel: one record of 5 V values per strip vector
+    // + one record of 8 values per z strip index
+    const size_t rimz_smem = (((size_t)(g.ivlo + ((int)(cdf_ld(g.nx, sizeof(T)) / g.v) - g.ivhi)) * 5 * g.v + 7) / 8 * 8 + (size_t)(2 * P.halo + 1) * 8) * sizeof(T);
     if (merged && !has_y && g.gx > 0 && nrim > 0) {
         const int nbulk = g.gx * g.gz;
 #define SWB_CDF_M(CT, AD, FM)                                                                            \
@@ -647,7 +1116,11 @@ void cd_fused_launch(const CdFusedParams<T> &P, const CdFusedGeom &g, bool adj, 
             check_launch("cd_bulk_kernel");                                             \
             count_launch();                                                             \
         }                                                                               \
-        if (nrim > 0) {                                                                 \
+        if (nrim > 0 && HY && g.rim_zc > 0) {                                           \
+            cd_rimz_kernel<T, CT, AD, FM><<<nrim, CDF_RIM_T, rimz_smem, st_rim>>>(P);   \
+            check_launch("cd_rimz_kernel");                                             \
+            count_launch();                                                             \
+        } else if (nrim > 0) {                                                          \
             cd_rim_kernel<T, CT, HY, AD, FM><<<nrim, CDF_RIM_T, 0, st_rim>>>(P);        \
             check_launch("cd_rim_kernel");                                              \
             count_launch();                                                             \

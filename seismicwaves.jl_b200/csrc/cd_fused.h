@@ -27,6 +27,17 @@ struct CdBox {
     long long start;    // index of the box's first vector in the rim enumeration
 };
 
+// March enumeration of a rim box (3D): a CTA owns a tile of tw x th (x-vector, row) columns and marches them over zc planes.
+// kind = the strip axis whose memory variables the march keeps one plane ahead in registers (0: x strips, 1: y strips, 2: the z
+// planes); strips of the other axes that cross the box (corners) are handled by the generic on-demand code.
+struct CdRimTile {
+    int tw, th;        // tile width (vectors) and height (rows), tw * th <= CDF_RIM_T
+    int ntx, nty, ntz; // tiles along x and y, chunks along z
+    int zc;            // planes per chunk
+    int cta0;          // first CTA of the box
+    int kind;
+};
+
 struct CdPointList {
     const int *off, *cell, *idx; // per-CTA CSR: entries [off[cta], off[cta+1]) = (in-CTA cell code, point index)
 };
@@ -41,6 +52,7 @@ struct CdFusedParams {
     // nz - 1 is a ghost plane the neighbour owns; this slab's kernels leave it alone.
     T *peer_lo, *peer_hi;
     int ghost_lo, ghost_hi;
+    int rim_skip;     // timing experiments only: bit k set = the marching rim kernel skips boxes of kind k (wrong results)
     int rim_prefetch; // 1: rim threads prefetch their C-PML memory variables before the first dependent use
     int rev; // 1: the bulk z chunks are issued from the last to the first (serpentine sweep: a step starts on the planes the previous one left in L2)
     long long ld, plane;   // row pitch and plane pitch (elements) of pcur / pold / pnew / fact / grad / stored fields
@@ -73,6 +85,7 @@ struct CdFusedParams {
     int nbox;
     CdBox box[CDF_MAX_BOX];
     long long nrimvec;
+    CdRimTile rt[CDF_MAX_BOX]; // march enumeration of the same boxes (cd_rimz_kernel)
 };
 
 // host-side geometry shared by the launcher and the code that builds the per-CTA point lists
@@ -86,10 +99,13 @@ struct CdFusedGeom {
     int nbox;
     CdBox box[CDF_MAX_BOX];
     long long nrimvec;
+    int rim_zc = 0;                     // > 0: the rim is marched along z in chunks of rim_zc planes (cd_rimz_kernel), 0: one thread per vector
+    CdRimTile rt[CDF_MAX_BOX];
+    int nrimz_cta = 0;
     int ncta_bulk() const { return (int)(gx * gy * gz); }
-    int ncta_rim() const { return (int)((nrimvec + CDF_RIM_T - 1) / CDF_RIM_T); }
+    int ncta_rim() const { return rim_zc > 0 ? nrimz_cta : (int)((nrimvec + CDF_RIM_T - 1) / CDF_RIM_T); }
 };
-CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool has_y, int zc, bool zpml_lo = true, bool zpml_hi = true);
+CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool has_y, int zc, bool zpml_lo = true, bool zpml_hi = true, int rim_zc = 0);
 // which kernel owns the 0-based cell (i, j, k): returns 0 (bulk) or 1 (rim), the CTA index in launch order and the packed in-CTA cell code
 int cd_fused_locate(const CdFusedGeom &g, int i, int j, int k, int *cta, int *code);
 template <class T>

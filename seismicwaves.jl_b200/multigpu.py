@@ -210,9 +210,17 @@ class _SlabSim:
                            recs=ScalarReceivers(local_positions(grec, irec), nt, dtype=self.params.dtype))
         return lshot, irec, grec.shape[0]
 
-    def run(self, lshot, irec, nrec_total) -> np.ndarray:
-        """runs the local shot; returns the (nt, nrec_total) matrix holding this slab's traces (zeros elsewhere)"""
-        self.sim.init_shot(lshot)
+    def run(self, lshot, irec, nrec_total, barrier=None) -> np.ndarray:
+        """runs the local shot; returns the (nt, nrec_total) matrix holding this slab's traces (zeros elsewhere).
+        `barrier` (slabs driven by threads of one process on one device): every slab binds its shot -- which may allocate, and
+        cudaMalloc / cudaFree wait for the whole device -- before any slab parks its stream on a neighbour's flag."""
+        try:
+            self.sim.init_shot(lshot)
+            if barrier is not None:
+                self.sim._bind(lshot)
+        finally:
+            if barrier is not None:
+                barrier.wait()
         self.sim.swforward_1shot(lshot)
         full = np.zeros((self.params.ntimesteps, nrec_total), dtype=self.params.dtype, order="F")
         if len(irec):
@@ -303,10 +311,11 @@ class SlabForwardLocal:
 
         prepared = [s.local_shot(shot) for s in self.slabs]
         out, err = [None] * self.n, [None] * self.n
+        barrier = threading.Barrier(self.n)
 
         def work(r):
             try:
-                out[r] = self.slabs[r].run(*prepared[r])
+                out[r] = self.slabs[r].run(*prepared[r], barrier=barrier)
             except Exception as e:  # noqa: BLE001
                 err[r] = e
 
