@@ -97,9 +97,10 @@ struct VdSmem {
 };
 
 // phase 1 of both tile bodies: the elected thread arms the mbarrier and requests every staged array of the tile as one TMA box
-// (zeros outside the padded planes); the caller waits on the barrier after its own register loads.
+// (zeros outside the padded planes); the caller waits on the barrier after its own register loads.  Two parts around the wait for
+// the previous step's grid (programmatic dependent launch): the material factors never change, the fields are that step's output.
 template <class T, int TY, bool ADJ>
-__device__ __forceinline__ void vd_stage_tma(const VdFusedParams<T> &P, T *sm, int x0, int y0)
+__device__ __forceinline__ void vd_stage_tma_material(const VdFusedParams<T> &P, T *sm, int x0, int y0)
 {
     typedef VdSmem<T, TY, ADJ> L;
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + L::BAR_OFF);
@@ -112,13 +113,22 @@ __device__ __forceinline__ void vd_stage_tma(const VdFusedParams<T> &P, T *sm, i
             bytes += (unsigned)((TY + 3) * SW * sizeof(T));
         mbar_expect_tx(bar, bytes);
         const int gb = PAD_GUARD_BEFORE;
-        tma_load_2d(sm + L::P_OFF, &P.tm[0], x0 - 8, gb + y0 - 3, bar);
-        tma_load_2d(sm + L::VX_OFF, &P.tm[1], x0 - 8, gb + y0, bar);
-        tma_load_2d(sm + L::VY_OFF, &P.tm[3], x0, gb + y0 - 2, bar);
         if (P.do_v) {
             tma_load_2d(sm + L::M1X_OFF, &P.tm[2], x0 - 8, gb + y0, bar);
             tma_load_2d(sm + L::M1Y_OFF, &P.tm[4], x0, gb + y0 - 2, bar);
         }
+    }
+}
+template <class T, int TY, bool ADJ>
+__device__ __forceinline__ void vd_stage_tma_fields(const VdFusedParams<T> &P, T *sm, int x0, int y0)
+{
+    typedef VdSmem<T, TY, ADJ> L;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + L::BAR_OFF);
+    if (threadIdx.x == 0) {
+        const int gb = PAD_GUARD_BEFORE;
+        tma_load_2d(sm + L::P_OFF, &P.tm[0], x0 - 8, gb + y0 - 3, bar);
+        tma_load_2d(sm + L::VX_OFF, &P.tm[1], x0 - 8, gb + y0, bar);
+        tma_load_2d(sm + L::VY_OFF, &P.tm[3], x0, gb + y0 - 2, bar);
         if (ADJ)
             tma_load_2d(sm + L::PI_OFF, &P.tm[5], x0 - 8, gb + y0 - 1, bar);
     }
@@ -419,7 +429,9 @@ __device__ __forceinline__ void vd_tile(const VdFusedParams<T> &P, unsigned char
     const int tile = trow * gridDim.x + blockIdx.x;
 
     // ---- phase 1: stage every input of the tile in shared memory (TMA) ---------------------------------------
-    vd_stage_tma<T, TY, ADJ>(P, sm, x0, y0);
+    vd_stage_tma_material<T, TY, ADJ>(P, sm, x0, y0);
+    pdl_wait(); // the previous step's grid has completed: its fields are visible
+    vd_stage_tma_fields<T, TY, ADJ>(P, sm, x0, y0);
     vd_stage_wait<T, TY, ADJ>(sm);
 
     // record_receivers!: traces[it, r] = p_in[rec]  (p_in is the pressure after the reference's step `rec_it`)
@@ -578,13 +590,15 @@ __device__ __forceinline__ void vd_tile_interior(const VdFusedParams<T> &P, unsi
     const int hc = lane < 2 ? lane - 2 - lane : NCH + (lane - 2) - lane; // chunk offset relative to this lane's own chunk
 
     // ---- phase 1: everything the tile needs goes into shared memory (TMA), m0 straight to registers ---------
-    vd_stage_tma<T, TY, ADJ>(P, sm, x0, y0);
+    vd_stage_tma_material<T, TY, ADJ>(P, sm, x0, y0);
     Chunk<T> m0r[TY / NW]; // m0 is used once per cell: in flight together with the TMA traffic
     if (P.do_p) {
 #pragma unroll
         for (int k = 0; k < TY / NW; ++k)
             m0r[k] = ldg_chunk(P.m0 + o + (long long)(w + NW * k) * ld);
     }
+    pdl_wait(); // the previous step's grid has completed: its fields are visible (the material requests above overlap its tail)
+    vd_stage_tma_fields<T, TY, ADJ>(P, sm, x0, y0);
     vd_stage_wait<T, TY, ADJ>(sm);
 
     if (P.rec_it > 0) { // record_receivers!
@@ -720,6 +734,7 @@ template <class T, class CT, bool ADJ, int TY>
 __global__ void __launch_bounds__(NTHR, sizeof(T) == 4 ? (ADJ ? 3 : 4) : 1) vd_fused_kernel(const __grid_constant__ VdFusedParams<T> P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_trigger(); // the next step's CTAs may take the SM slots this grid frees while it drains
     const int x0 = blockIdx.x * TX, y0 = vd_tile_row<TY>(P.halo, P.rev) * TY, h = P.halo;
     // block-uniform: does the tile (with the halo it recomputes) touch a C-PML strip or the grid edge?
     const bool edge = (x0 - 8 <= h + 2) || (x0 + TX + 8 >= P.nx - h - 2) || (y0 - 4 <= h + 2) || (y0 + TY + 4 >= P.ny - h - 2);
@@ -741,7 +756,16 @@ void launch_one(const VdFusedParams<T> &P, cudaStream_t st)
         configured = true;
     }
     dim3 grd(cdiv(P.nx, TX), cdiv(P.ny, TY), 1);
-    kern<<<grd, NTHR, smem, st>>>(P);
+    if (pdl_enabled()) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grd, cfg.blockDim = dim3(NTHR, 1, 1), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at, cfg.numAttrs = 1;
+        SWB_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+    } else
+        kern<<<grd, NTHR, smem, st>>>(P);
     check_launch("vd_fused");
     count_launch();
 }

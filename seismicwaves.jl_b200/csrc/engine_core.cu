@@ -10,6 +10,12 @@
 #include "tma.cuh"
 namespace swb {
 
+bool pdl_enabled()
+{
+    static const bool on = std::getenv("SWB_NO_PDL") == nullptr;
+    return on;
+}
+
 void make_tmap_2d(CUtensorMap *out, int dtype, const void *base, long long ld, long long rows, int box_w, int box_h)
 {
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,

@@ -11,8 +11,16 @@ namespace swb {
 // tensor map of a 2D row-major plane of `rows` rows with row pitch `ld` elements (dtype SWB_F32 / SWB_F64), box = box_w x box_h
 // elements, no swizzle, zero fill outside the plane.  Host side (engine_core.cu); throws swb::Error.
 void make_tmap_2d(CUtensorMap *out, int dtype, const void *base, long long ld, long long rows, int box_w, int box_h);
+// false when SWB_NO_PDL is set: the step kernels are then launched with full stream serialization
+bool pdl_enabled();
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (consecutive step kernels of a sweep): a kernel launched with launch_pdl() may start while its
+// predecessor on the stream drains; it must call pdl_wait() before it touches anything the predecessor writes (everything it requests
+// before that -- material arrays -- overlaps the predecessor's tail and its own launch latency).  pdl_trigger() lets the successor's
+// CTAs be scheduled as soon as every CTA of this grid has started.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
