@@ -351,17 +351,19 @@ __device__ __forceinline__ void cd_axis_term_vec(CT (&term)[V], const CT (&w1)[2
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
-__device__ __forceinline__ void cd_rim_body(const CdFusedParams<T> &P, const int cta, const int tid)
+__device__ __forceinline__ void cd_rim_body(const CdFusedParams<T> &P, const int ecta, const int tid, const int nbox, const long long nrimvec, const int cta0 = 0)
 {
+    // ecta: CTA index in the enumeration of the first nbox boxes (nrimvec vectors); cta: its number in the point lists
     constexpr int V = 16 / (int)sizeof(T);
     typedef CVec<T, V> VT;
-    const long long vid = (long long)cta * CDF_RIM_T + tid;
-    if (vid >= P.nrimvec)
+    const int cta = cta0 + ecta;
+    const long long vid = (long long)ecta * CDF_RIM_T + tid;
+    if (vid >= nrimvec)
         return;
     int bi = 0;
 #pragma unroll
     for (int b = 1; b < CDF_MAX_BOX; ++b)
-        if (b < P.nbox && vid >= P.box[b].start)
+        if (b < nbox && vid >= P.box[b].start)
             bi = b;
     const CdBox &B = P.box[bi];
     const unsigned loc = (unsigned)(vid - B.start); // a box holds fewer than 2^31 vectors (checked on the host)
@@ -497,7 +499,11 @@ __device__ __forceinline__ void cd_rim_body(const CdFusedParams<T> &P, const int
 template <class T, class CT, bool HAS_Y, bool ADJ, bool FMA>
 __global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? CDF_RIM_MINB : CDF_RIM_MINB / 2) cd_rim_kernel(const CdFusedParams<T> P)
 {
-    cd_rim_body<T, CT, HAS_Y, ADJ, FMA>(P, (int)blockIdx.x, (int)threadIdx.x);
+    // (3D with the march: only the leading z-plane boxes, numbered after the march's CTAs in the point lists)
+    if (HAS_Y && P.nbox_v > 0)
+        cd_rim_body<T, CT, HAS_Y, ADJ, FMA>(P, (int)blockIdx.x, (int)threadIdx.x, P.nbox_v, P.nrimvec_v, P.rimv_cta0);
+    else
+        cd_rim_body<T, CT, HAS_Y, ADJ, FMA>(P, (int)blockIdx.x, (int)threadIdx.x, P.nbox, P.nrimvec);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -918,10 +924,10 @@ __global__ void __launch_bounds__(CDF_RIM_T, CDF_RIMZ_MINB) cd_rimz_kernel(const
 {
     constexpr int V = 16 / (int)sizeof(T);
     const int cta = (int)blockIdx.x;
-    int bi = 0;
+    int bi = P.nbox_v; // (the z-plane boxes in front belong to the per-vector kernel)
 #pragma unroll
     for (int b = 1; b < CDF_MAX_BOX; ++b)
-        if (b < P.nbox && cta >= P.rt[b].cta0)
+        if (b > P.nbox_v && b < P.nbox && cta >= P.rt[b].cta0)
             bi = b;
     const CdBox &B = P.box[bi];
     const CdRimTile &R = P.rt[bi];
@@ -931,14 +937,12 @@ __global__ void __launch_bounds__(CDF_RIM_T, CDF_RIMZ_MINB) cd_rimz_kernel(const
     extern __shared__ __align__(16) unsigned char cdf_smem[];
     T *xtab = reinterpret_cast<T *>(cdf_smem);
     T *ztab = xtab + (cd_xtab_records<T, V>(P) * 5 * V + 7) / 8 * 8;
-    cd_rimz_tables<T, V>(P, xtab, ztab, R.kind == 2, (int)threadIdx.x, CDF_RIM_T);
+    cd_rimz_tables<T, V>(P, xtab, ztab, false, (int)threadIdx.x, CDF_RIM_T);
     __syncthreads();
     if (R.kind == 0)
         cd_rimz_body<T, CT, 0, ADJ, FMA>(P, B, R, local, cta, (int)threadIdx.x, xtab, ztab);
-    else if (R.kind == 1)
-        cd_rimz_body<T, CT, 1, ADJ, FMA>(P, B, R, local, cta, (int)threadIdx.x, xtab, ztab);
     else
-        cd_rimz_body<T, CT, 2, ADJ, FMA>(P, B, R, local, cta, (int)threadIdx.x, xtab, ztab);
+        cd_rimz_body<T, CT, 1, ADJ, FMA>(P, B, R, local, cta, (int)threadIdx.x, xtab, ztab);
 }
 
 // Small 2D grids: both CTA kinds in one launch (the 2D bulk CTA and the rim CTA have 128 threads each).  A step of a grid that
@@ -952,7 +956,7 @@ __global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? 8 : 4) cd_merged2
     if (b < nbulk)
         cd_bulk_body<T, CT, false, ADJ, FMA>(P, b % gdx, 0, P.rev ? nbulk / gdx - 1 - b / gdx : b / gdx, gdx, 1, CDF_W2D, (int)threadIdx.x & 31, (int)threadIdx.x >> 5);
     else
-        cd_rim_body<T, CT, false, ADJ, FMA>(P, b - nbulk, (int)threadIdx.x);
+        cd_rim_body<T, CT, false, ADJ, FMA>(P, b - nbulk, (int)threadIdx.x, P.nbox, P.nrimvec);
 }
 
 } // namespace
@@ -998,7 +1002,13 @@ CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool h
         CdBox &b = g.box[g.nbox++];
         b.iv0 = iv0, b.j0 = j0, b.k0 = k0, b.nvx = nvx, b.ny = nyb, b.nz = nzb, b.start = start;
         start += (long long)nvx * nyb * nzb;
-        if (g.rim_zc > 0) { // march enumeration: tiles of columns x chunks of planes
+        if (g.rim_zc > 0 && kind == 2) { // stays with the per-vector kernel (added first: its enumeration is a prefix of the box list)
+            g.nbox_v = g.nbox;
+            g.nrimvec_v = start;
+            t = CdRimTile{};
+            t.kind = 2;
+            t.cta0 = 0x7fffffff;
+        } else if (g.rim_zc > 0) { // march enumeration: tiles of columns x chunks of planes
             t.tw = std::min(nvx, 32);
             t.th = std::min(CDF_RIM_T / t.tw, nyb);
             t.ntx = (nvx + t.tw - 1) / t.tw;
@@ -1050,6 +1060,12 @@ int cd_fused_locate(const CdFusedGeom &g, int i, int j, int k, int *cta, int *co
     for (int b = 0; b < g.nbox; ++b) {
         const CdBox &B = g.box[b];
         if (iv >= B.iv0 && iv < B.iv0 + B.nvx && j >= B.j0 && j < B.j0 + B.ny && k >= B.k0 && k < B.k0 + B.nz) {
+            if (g.rim_zc > 0 && b < g.nbox_v) { // z-plane box: per-vector kernel, CTAs numbered after the march's
+                const long long lin = B.start + ((long long)(k - B.k0) * B.ny + (j - B.j0)) * B.nvx + (iv - B.iv0);
+                *cta = g.nrimz_cta + (int)(lin / CDF_RIM_T);
+                *code = (int)(lin % CDF_RIM_T) * g.v + i % g.v;
+                return 1;
+            }
             if (g.rim_zc > 0) {
                 const CdRimTile &R = g.rt[b];
                 const int ivl = iv - B.iv0, jl = j - B.j0, kl = k - B.k0;
@@ -1077,6 +1093,7 @@ void cd_fused_fill_geom(CdFusedParams<T> &P, const CdFusedGeom &g)
     P.nrimvec = g.nrimvec;
     for (int b = 0; b < g.nbox; ++b)
         P.rt[b] = g.rt[b];
+    P.nbox_v = g.rim_zc > 0 ? g.nbox_v : 0, P.nrimvec_v = g.nrimvec_v, P.rimv_cta0 = g.nrimz_cta;
 }
 
 template <class T>
@@ -1117,9 +1134,16 @@ void cd_fused_launch(const CdFusedParams<T> &P, const CdFusedGeom &g, bool adj, 
             count_launch();                                                             \
         }                                                                               \
         if (nrim > 0 && HY && g.rim_zc > 0) {                                           \
-            cd_rimz_kernel<T, CT, AD, FM><<<nrim, CDF_RIM_T, rimz_smem, st_rim>>>(P);   \
-            check_launch("cd_rimz_kernel");                                             \
-            count_launch();                                                             \
+            if (g.ncta_rimv() > 0) {                                                    \
+                cd_rim_kernel<T, CT, HY, AD, FM><<<g.ncta_rimv(), CDF_RIM_T, 0, st_rim>>>(P); \
+                check_launch("cd_rim_kernel");                                          \
+                count_launch();                                                         \
+            }                                                                           \
+            if (g.nrimz_cta > 0) {                                                      \
+                cd_rimz_kernel<T, CT, AD, FM><<<g.nrimz_cta, CDF_RIM_T, rimz_smem, st_rim>>>(P); \
+                check_launch("cd_rimz_kernel");                                         \
+                count_launch();                                                         \
+            }                                                                           \
         } else if (nrim > 0) {                                                          \
             cd_rim_kernel<T, CT, HY, AD, FM><<<nrim, CDF_RIM_T, 0, st_rim>>>(P);        \
             check_launch("cd_rim_kernel");                                              \

@@ -85,7 +85,12 @@ struct CdFusedParams {
     int nbox;
     CdBox box[CDF_MAX_BOX];
     long long nrimvec;
-    CdRimTile rt[CDF_MAX_BOX]; // march enumeration of the same boxes (cd_rimz_kernel)
+    CdRimTile rt[CDF_MAX_BOX]; // march enumeration of the x / y strip boxes (cd_rimz_kernel)
+    // 3D with the march: the z-plane boxes (the first nbox_v boxes, nrimvec_v vectors) stay with the one-thread-per-vector kernel -- whole
+    // planes have all the parallelism it wants, and a march over the 20 planes of a strip is latency-bound (768^3: 0.15 ms against 0.10);
+    // its CTAs are numbered after the march's in the point lists (rimv_cta0)
+    int nbox_v, rimv_cta0;
+    long long nrimvec_v;
 };
 
 // host-side geometry shared by the launcher and the code that builds the per-CTA point lists
@@ -101,9 +106,12 @@ struct CdFusedGeom {
     long long nrimvec;
     int rim_zc = 0;                     // > 0: the rim is marched along z in chunks of rim_zc planes (cd_rimz_kernel), 0: one thread per vector
     CdRimTile rt[CDF_MAX_BOX];
-    int nrimz_cta = 0;
+    int nrimz_cta = 0;                  // CTAs of the march (x / y strip boxes)
+    int nbox_v = 0;                     // with the march: the leading z-plane boxes, run by the per-vector kernel
+    long long nrimvec_v = 0;
     int ncta_bulk() const { return (int)(gx * gy * gz); }
-    int ncta_rim() const { return rim_zc > 0 ? nrimz_cta : (int)((nrimvec + CDF_RIM_T - 1) / CDF_RIM_T); }
+    int ncta_rimv() const { return (int)(((rim_zc > 0 ? nrimvec_v : nrimvec) + CDF_RIM_T - 1) / CDF_RIM_T); }
+    int ncta_rim() const { return rim_zc > 0 ? nrimz_cta + ncta_rimv() : ncta_rimv(); }
 };
 CdFusedGeom cd_fused_geom(size_t esize, int nx, int ny, int nz, int halo, bool has_y, int zc, bool zpml_lo = true, bool zpml_hi = true, int rim_zc = 0);
 // which kernel owns the 0-based cell (i, j, k): returns 0 (bulk) or 1 (rim), the CTA index in launch order and the packed in-CTA cell code
