@@ -58,6 +58,14 @@ const char *swb_abi_layout(void);
 int32_t swb_device_count(void);
 /* kernel launches issued by this process through the library so far (bench.py's gpu_launches) */
 int64_t swb_launch_count(void);
+/* Host-only self check (no device needed) of how the fused acoustic CD step divides an (nx, ny, nz) grid among its kernels -- the
+ * register-queue march of the interior, the z-marched x / y strip boxes and the per-vector strips / faces (a 2D
+ * grid (nx, nz2d) is passed as (nx, 1, nz2d)): every cell must be owned by exactly one (kernel, CTA, in-CTA slot) and every slot must
+ * lie inside its CTA's range, because the per-CTA source / receiver lists address cells that way.  esize = 4 / 8; zc = planes per bulk
+ * chunk; zpml_lo / zpml_hi = 0 for a z end without C-PML strip (free surface, interior face of a z slab); rim_zc = planes per chunk
+ * of the rim march (< 0: the engine's default, 0: no march).  counts[3] receives the cells owned by the three kernel kinds. */
+int32_t swb_diag_cd_partition(int32_t esize, int32_t nx, int32_t ny, int32_t nz, int32_t halo, int32_t zc, int32_t zpml_lo, int32_t zpml_hi,
+                              int32_t rim_zc, int64_t *counts);
 
 /* ---------------------------------------------------------------------------------------------
  * 1. Device buffers -- backs the Julia `B200Array{T,N}` that plays the role of backend.Data.Array /

@@ -111,7 +111,7 @@ class swb_slab_handle(C.Structure):
 
 # every symbol include/swb200.h declares (tests check the header against this list and the .so against both)
 EXPORTS = [
-    "swb_last_error", "swb_abi_version", "swb_abi_layout", "swb_device_count", "swb_launch_count",
+    "swb_last_error", "swb_abi_version", "swb_abi_layout", "swb_device_count", "swb_launch_count", "swb_diag_cd_partition",
     "swb_set_device", "swb_malloc", "swb_free", "swb_memcpy_h2d", "swb_memcpy_d2h", "swb_memcpy_d2d", "swb_fill", "swb_synchronize",
     "swb_acou_cd_forward_onestep", "swb_acou_cd_adjoint_onestep", "swb_acou_cd_correlate_gradient", "swb_prescale_residuals",
     "swb_acou_vd_forward_onestep", "swb_acou_vd_adjoint_onestep", "swb_acou_vd_correlate_gradient_m0", "swb_acou_vd_correlate_gradient_m1",
@@ -150,6 +150,7 @@ def load() -> C.CDLL:
     lib.swb_sim_cell_updates.argtypes = [C.c_void_p]
     vp, i32, i64, dbl, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_size_t
     sigs = {
+        "swb_diag_cd_partition": [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(i64)],
         "swb_set_device": [i32],
         "swb_malloc": [C.POINTER(vp), sz],
         "swb_free": [vp],

@@ -522,18 +522,15 @@ __global__ void __launch_bounds__(CDF_RIM_T, sizeof(CT) == 4 ? CDF_RIM_MINB : CD
 // computed.  Strips of the other axes that cross a box (edges and corners of the grid) fetch their memory variables on demand.
 // Values are those of cd_rim_body operation for operation.
 
-// one cell, one axis of @∇̃² with preloaded memory variables (same operations as cd_axis_term / cd_axis_term_vec);
-// lo_given: psi_lo already holds the new value (computed by the previous plane of a z march)
+// one cell, one axis of @∇̃² with preloaded memory variables (same operations as cd_axis_term / cd_axis_term_vec)
 template <class T, class CT>
 __device__ __forceinline__ CT cd_axis_cell(const CT (&w1)[2], CT D2, CT lo, CT mid, CT hi, T inv, T ah1, T bh1, T ah0, T bh0, T a1, T b1, T ph, T pl, T xo,
-                                           T &psi_hi, T &psi_lo, T &xn, bool lo_given = false)
+                                           T &psi_hi, T &psi_lo, T &xn)
 {
     const CT Dhi = (w1[0] * mid + w1[1] * hi) * (CT)inv;
     (void)cpml_apply<T, CT>(Dhi, ah1, bh1, ph, psi_hi);
-    if (!lo_given) {
-        const CT Dlo = (w1[0] * lo + w1[1] * mid) * (CT)inv;
-        (void)cpml_apply<T, CT>(Dlo, ah0, bh0, pl, psi_lo);
-    }
+    const CT Dlo = (w1[0] * lo + w1[1] * mid) * (CT)inv;
+    (void)cpml_apply<T, CT>(Dlo, ah0, bh0, pl, psi_lo);
     const CT dpsi = (w1[0] * (CT)psi_lo + w1[1] * (CT)psi_hi) * (CT)inv;
     const T bx = b1 * xo;
     xn = (T)((CT)bx + (CT)a1 * (D2 + dpsi));
@@ -567,17 +564,11 @@ __device__ __forceinline__ int cd_xstrip_need(int xm)
 {
     return (xm | (xm << 1)) & ((1 << (V + 1)) - 1);
 }
-// per-CTA tables in shared memory.  x: record r (5 V values) of x-strip vector r: a_h[e], e < V | b_h[e], e < V | a[v] | b[v] | a_h[V], b_h[V];
-// z: record s (8 values) of strip index s: a_h[s-1], b_h[s-1], a_h[s-2], b_h[s-2], a[s-1], b[s-1]
+// per-CTA table in shared memory: record r (5 V values) of x-strip vector r: a_h[e], e < V | b_h[e], e < V | a[v] | b[v] | a_h[V], b_h[V]
 template <class T, int V>
-__device__ __forceinline__ int cd_xtab_records(const CdFusedParams<T> &P)
+__device__ __forceinline__ void cd_xstrip_table(const CdFusedParams<T> &P, T *xtab, int tid, int nthreads)
 {
-    return P.ivlo + ((int)(P.ld / V) - P.ivhi);
-}
-template <class T, int V>
-__device__ __forceinline__ void cd_rimz_tables(const CdFusedParams<T> &P, T *xtab, T *ztab, bool with_z, int tid, int nthreads)
-{
-    const int nrec = cd_xtab_records<T, V>(P);
+    const int nrec = P.ivlo + ((int)(P.ld / V) - P.ivhi);
     for (int r = tid; r < nrec; r += nthreads) {
         const int iv = r < P.ivlo ? r : P.ivhi + (r - P.ivlo);
         int s0, xm, xf;
@@ -598,11 +589,6 @@ __device__ __forceinline__ void cd_rimz_tables(const CdFusedParams<T> &P, T *xta
             q[3 * V + v] = on ? P.b[0][s0 - 1 + v] : (T)0;
         }
     }
-    if (with_z)
-        for (int s = 2 + tid; s <= 2 * P.halo; s += nthreads) {
-            T *q = ztab + s * 8;
-            q[0] = P.a_h[2][s - 1], q[1] = P.b_h[2][s - 1], q[2] = P.a_h[2][s - 2], q[3] = P.b_h[2][s - 2], q[4] = P.a[2][s - 1], q[5] = P.b[2][s - 1];
-        }
 }
 
 // x term of @∇̃² for the V cells of a strip vector.  psv[e] = psi_in[s0 - 2 + e], xiv[v] = xi[s0 - 1 + v] (already loaded);
@@ -654,13 +640,14 @@ template <class T, int V>
 struct RimPre { // what a march thread requests one plane ahead
     CVec<T, V> po, fc, yu, yd; // pold, fact, pcur of rows j - 1 and j + 1
     T xl, xr;                  // pcur of the cells left and right of the vector
-    CVec<T, V> ph, pl, xo;     // own strip axis y / z: psi[s - 1], psi[s - 2] (y only), xi[s - 1]
+    CVec<T, V> ph, pl, xo;     // y-strip box: psi_y[sy - 1], psi_y[sy - 2], xi_y[sy - 1]
     T psv[V + 1], xiv[V];      // own strip axis x: psi_x[s0 - 2 ..], xi_x[s0 - 1 ..]
 };
 
+// KIND 0: an x-strip box (rows and planes of the bulk), KIND 1: a y-strip box (all x: its corner columns cross the x strips)
 template <class T, class CT, int KIND, bool ADJ, bool FMA>
 __device__ __forceinline__ void cd_rimz_body(const CdFusedParams<T> &P, const CdBox &B, const CdRimTile &R, const int local, const int cta, const int tid,
-                                             const T *xtab, const T *ztab)
+                                             const T *xtab)
 {
     constexpr int V = 16 / (int)sizeof(T);
     typedef CVec<T, V> VT;
@@ -671,7 +658,7 @@ __device__ __forceinline__ void cd_rimz_body(const CdFusedParams<T> &P, const Cd
     if (lj >= R.th || ivl >= B.nvx || jl >= B.ny)
         return; // no barriers below, no shuffles: threads leave freely
     const int iv = B.iv0 + ivl, j = B.j0 + jl, i0 = iv * V;
-    const int k0 = B.k0 + tz_ * R.zc, k1 = min(k0 + R.zc, B.k0 + B.nz); // KIND 0 / 1: interior planes only, 1 <= k <= nz - 2
+    const int k0 = B.k0 + tz_ * R.zc, k1 = min(k0 + R.zc, B.k0 + B.nz); // interior planes only: 1 <= k <= nz - 2, no z strip
     const int nx = P.nx, ny = P.ny, nz = P.nz, h = P.halo;
     const long long ld = P.ld, plane = P.plane;
     const bool has_inj = P.inj_it > 0 && P.inj[1].off[cta + 1] > P.inj[1].off[cta];
@@ -681,8 +668,7 @@ __device__ __forceinline__ void cd_rimz_body(const CdFusedParams<T> &P, const Cd
     for (int v = 0; v < V; ++v)
         if (i0 + v >= 1 && i0 + v <= nx - 2)
             okm |= 1 << v;
-    const long long col = (long long)j * ld + i0;
-    long long off = (long long)k0 * plane + col;
+    long long off = (long long)k0 * plane + (long long)j * ld + i0;
 
     auto finish = [&](int k, long long o, VT out, const VT &c2, const VT &c1, const VT &c0, VT g) {
         const int code0 = ((k - k0) * CDF_RIM_T + tid) * V;
@@ -702,55 +688,43 @@ __device__ __forceinline__ void cd_rimz_body(const CdFusedParams<T> &P, const Cd
             stv<T, V>(P.grad + o, g);
         }
     };
-    auto copy_plane = [&](int k, long long o) { // a face cell is never updated (pnew aliases pold in the reference)
-        if (KIND == 2 && ((k == 0 && P.ghost_lo) || (k == nz - 1 && P.ghost_hi)))
-            return; // ghost plane of a z slab: written by the neighbour that owns it
-        VT c2 = {}, c1 = {}, c0 = {}, g = {};
-        if (ADJ) {
-            c2 = ldv<T, V>(P.pm2 + o);
-            c1 = ldv<T, V>(P.pm1 + o);
-            c0 = ldv<T, V>(P.p0 + o);
-            g = ldv<T, V>(P.grad + o);
-        }
-        finish(k, o, ldv<T, V>(P.pold + o), c2, c1, c0, g);
-    };
 
-    if (KIND != 0 && !(j >= 1 && j <= ny - 2)) { // a y face row
+    if (KIND == 1 && !(j >= 1 && j <= ny - 2)) { // a y face row is never updated (pnew aliases pold in the reference)
 #pragma unroll 1
-        for (int k = k0; k < k1; ++k, off += plane)
-            copy_plane(k, off);
+        for (int k = k0; k < k1; ++k, off += plane) {
+            VT c2 = {}, c1 = {}, c0 = {}, g = {};
+            if (ADJ) {
+                c2 = ldv<T, V>(P.pm2 + off);
+                c1 = ldv<T, V>(P.pm1 + off);
+                c0 = ldv<T, V>(P.p0 + off);
+                g = ldv<T, V>(P.grad + off);
+            }
+            finish(k, off, ldv<T, V>(P.pold + off), c2, c1, c0, g);
+        }
         return;
     }
 
     const CT w1[2] = {(CT)P.c1[0], (CT)P.c1[1]};
     const CT w2[3] = {(CT)P.c2[0], (CT)P.c2[1], (CT)P.c2[2]};
     const CT i2x = (CT)(P.inv_d[0] * P.inv_d[0]), i2y = (CT)(P.inv_d[1] * P.inv_d[1]), i2z = (CT)(P.inv_d[2] * P.inv_d[2]);
-    // x strip of this vector (KIND 0: the box itself; KIND 1 / 2: the columns where the box crosses the x strips)
+    // x strip of this vector (KIND 0: the box itself; KIND 1: the columns where the box crosses the x strips)
     int s0, xm, xfirst;
     cd_xstrip_desc<V>(i0, nx, h, s0, xm, xfirst);
     const int xneed = cd_xstrip_need<V>(xm);
     const T *xrec = xtab + (iv < P.ivlo ? iv : P.ivlo + (iv - P.ivhi)) * (5 * V);
     const long long xpinc = (long long)ny * (2 * h), xxinc = (long long)ny * (2 * (h + 1));
     long long xpo = ((long long)k0 * ny + j) * (2 * h) + (s0 - 2), xxo = ((long long)k0 * ny + j) * (2 * (h + 1)) + (s0 - 1);
-    // y strip of this row (KIND 1: the box itself; KIND 2: the rows where the z planes cross the y strips)
-    const int sy = (KIND != 0 && h > 0) ? strip_index(j + 1, ny, h) : 0;
+    // y strip of this row (KIND 1)
+    const int sy = (KIND == 1 && h > 0) ? strip_index(j + 1, ny, h) : 0;
     T yah1 = (T)0, ybh1 = (T)0, yah0 = (T)0, ybh0 = (T)0, ya1 = (T)0, yb1 = (T)0;
-    if (KIND != 0 && sy > 0)
+    if (KIND == 1 && sy > 0)
         yah1 = P.a_h[1][sy - 1], ybh1 = P.b_h[1][sy - 1], yah0 = P.a_h[1][sy - 2], ybh0 = P.b_h[1][sy - 2], ya1 = P.a[1][sy - 1], yb1 = P.b[1][sy - 1];
     const bool ylo_store = j + 1 == 2 || j + 1 == ny - h + 1;
     const long long ypinc = ld * (2 * h), yxinc = ld * (2 * (h + 1));
     long long ypo = (long long)k0 * ypinc + i0 + (long long)(sy - 2) * ld, yxo_ = (long long)k0 * yxinc + i0 + (long long)(sy - 1) * ld;
-    // z strip (KIND 2): active strip index of plane k (0: plain or face)
-    const long long zst = ld * ny;
-    auto z_index = [&](int k) -> int {
-        if (KIND != 2 || h <= 0 || k < 1 || k > nz - 2)
-            return 0;
-        const int sz = strip_index(k + 1, nz, h);
-        return (sz > 0 && (sz <= h ? P.zpml_lo != 0 : P.zpml_hi != 0)) ? sz : 0;
-    };
 
-    // requests of plane kn (always a valid plane; KIND 2: possibly a face)
-    auto load_pre = [&](Pre &q, int kn, long long o, long long xp, long long xx, long long yp, long long yx) {
+    // requests of one plane
+    auto load_pre = [&](Pre &q, long long o, long long xp, long long xx, long long yp, long long yx) {
         q.po = ldv<T, V>(P.pold + o);
         q.fc = ldv<T, V>(P.fact + o);
         q.yu = ldv<T, V>(P.pcur + o - ld);
@@ -775,37 +749,25 @@ __device__ __forceinline__ void cd_rimz_body(const CdFusedParams<T> &P, const Cd
             q.ph = ldv<T, V>(P.psi_in[1] + yp + ld);
             q.xo = ldv<T, V>(P.xi[1] + yx);
         }
-        if (KIND == 2) {
-            const int sz = z_index(kn);
-            if (sz > 0) {
-                q.ph = ldv<T, V>(P.psi_in[2] + col + (long long)(sz - 1) * zst);
-                q.xo = ldv<T, V>(P.xi[2] + col + (long long)(sz - 1) * zst);
-            }
-        }
     };
 
-    // queue: rows j +- 1 exist (y faces left above), planes are clamped into the grid (a clamped value is only seen by a face plane)
-    VT qm = ldv<T, V>(P.pcur + off - (k0 >= 1 ? plane : 0)), qc = ldv<T, V>(P.pcur + off), qp = ldv<T, V>(P.pcur + off + (k0 + 1 <= nz - 1 ? plane : 0));
+    VT qm = ldv<T, V>(P.pcur + off - plane), qc = ldv<T, V>(P.pcur + off), qp = ldv<T, V>(P.pcur + off + plane);
     Pre A = {}, Bf = {};
-    load_pre(A, k0, off, xpo, xxo, ypo, yxo_);
-    VT zcarry = {};     // KIND 2: the new psi_z[s - 1] of the previous plane = psi_lo of this one
-    bool zhave = false;
+    load_pre(A, off, xpo, xxo, ypo, yxo_);
 
     auto iter = [&](const int k, Pre &cur, Pre &nxt) {
         const bool more = k + 1 < k1; // the last plane re-requests itself (cache hits) instead of predicating every prefetch
         const long long dn = more ? plane : 0;
-        const bool zface = KIND == 2 && (k < 1 || k > nz - 2);
-        const int sz = z_index(k);
         // L1TEX returns a warp's loads in order: what this plane still has to fetch itself goes out before the prefetch of the next one
         VT c2 = {}, c1 = {}, c0 = {}, g = {};
-        if (ADJ && !zface) {
+        if (ADJ) {
             c2 = ldv<T, V>(P.pm2 + off);
             c1 = ldv<T, V>(P.pm1 + off);
             c0 = ldv<T, V>(P.p0 + off);
             g = ldv<T, V>(P.grad + off);
         }
-        T cpsv[V + 1], cxiv[V]; // the box crosses an x strip here (KIND 1 / 2): memory variables on demand
-        if (KIND != 0 && xm != 0 && !zface) {
+        T cpsv[V + 1], cxiv[V]; // a y-strip box crossing an x strip: those memory variables on demand
+        if (KIND != 0 && xm != 0) {
             const T *ps = P.psi_in[0] + xpo, *xs = P.xi[0] + xxo;
 #pragma unroll
             for (int e = 0; e <= V; ++e)
@@ -814,94 +776,56 @@ __device__ __forceinline__ void cd_rimz_body(const CdFusedParams<T> &P, const Cd
             for (int v = 0; v < V; ++v)
                 cxiv[v] = ((xm >> v) & 1) ? xs[v] : (T)0;
         }
-        VT yph = cur.ph, ypl = cur.pl, yxo = cur.xo, zpl = zcarry;
-        if (KIND == 2 && !zface) {
-            if (sy > 0) { // z planes crossing a y strip
-                ypl = ldv<T, V>(P.psi_in[1] + ypo);
-                yph = ldv<T, V>(P.psi_in[1] + ypo + ld);
-                yxo = ldv<T, V>(P.xi[1] + yxo_);
+        const VT qn = ldv<T, V>(P.pcur + off + dn + plane);
+        load_pre(nxt, off + dn, xpo + (more ? xpinc : 0), xxo + (more ? xxinc : 0), ypo + (more ? ypinc : 0), yxo_ + (more ? yxinc : 0));
+        const T xl_in = cur.xl, xr_in = cur.xr;
+        CT pc[V], lap[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            pc[v] = (CT)qc.v[v];
+        // ---- x term ----------------------------------------------------------------------------------------------------
+        if (KIND == 0)
+            cd_xstrip_vec<T, CT, V, FMA>(lap, w1, w2, qc, xl_in, xr_in, P.inv_d[0], xm, xfirst, xrec, cur.psv, cur.xiv, P.psi_out[0] + xpo, P.xi[0] + xxo);
+        else if (xm != 0)
+            cd_xstrip_vec<T, CT, V, FMA>(lap, w1, w2, qc, xl_in, xr_in, P.inv_d[0], xm, xfirst, xrec, cpsv, cxiv, P.psi_out[0] + xpo, P.xi[0] + xxo);
+        else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const CT xl = (CT)(v > 0 ? qc.v[v > 0 ? v - 1 : 0] : xl_in);
+                const CT xr = (CT)(v < V - 1 ? qc.v[v < V - 1 ? v + 1 : 0] : xr_in);
+                lap[v] = d2<CT, FMA>(w2, xl, pc[v], xr, i2x);
             }
-            if (sz > 0 && !zhave) // first strip plane of this march
-                zpl = ldv<T, V>(P.psi_in[2] + col + (long long)(sz - 2) * zst);
         }
-        const VT qn = ldv<T, V>(P.pcur + off + dn + ((KIND != 2 || k + (more ? 2 : 1) <= nz - 1) ? plane : 0));
-        load_pre(nxt, more ? k + 1 : k, off + dn, xpo + (more ? xpinc : 0), xxo + (more ? xxinc : 0), ypo + (more ? ypinc : 0), yxo_ + (more ? yxinc : 0));
-        if (zface) {
-            copy_plane(k, off);
-            zhave = false;
-        } else {
-            const T xl_in = cur.xl, xr_in = cur.xr;
-            CT pc[V], lap[V];
+        // ---- y term ----------------------------------------------------------------------------------------------------
+        if (KIND != 0 && sy > 0) {
+            const VT ph = cur.ph, pl = cur.pl, xo = cur.xo;
+            VT psi_hi = ph, psi_lo = pl, xn = xo;
 #pragma unroll
-            for (int v = 0; v < V; ++v)
-                pc[v] = (CT)qc.v[v];
-            // ---- x term ------------------------------------------------------------------------------------------------
-            if (KIND == 0)
-                cd_xstrip_vec<T, CT, V, FMA>(lap, w1, w2, qc, xl_in, xr_in, P.inv_d[0], xm, xfirst, xrec, cur.psv, cur.xiv, P.psi_out[0] + xpo, P.xi[0] + xxo);
-            else if (xm != 0)
-                cd_xstrip_vec<T, CT, V, FMA>(lap, w1, w2, qc, xl_in, xr_in, P.inv_d[0], xm, xfirst, xrec, cpsv, cxiv, P.psi_out[0] + xpo, P.xi[0] + xxo);
-            else {
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    const CT xl = (CT)(v > 0 ? qc.v[v > 0 ? v - 1 : 0] : xl_in);
-                    const CT xr = (CT)(v < V - 1 ? qc.v[v < V - 1 ? v + 1 : 0] : xr_in);
-                    lap[v] = d2<CT, FMA>(w2, xl, pc[v], xr, i2x);
-                }
-            }
-            // ---- y term ------------------------------------------------------------------------------------------------
-            if (KIND != 0 && sy > 0) {
-                const VT ph = yph, pl = ypl, xo = yxo;
-                VT psi_hi = ph, psi_lo = pl, xn = xo;
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    CT t = d2<CT, FMA>(w2, (CT)cur.yu.v[v], pc[v], (CT)cur.yd.v[v], i2y);
-                    if ((okm >> v) & 1)
-                        t = cd_axis_cell<T, CT>(w1, t, (CT)cur.yu.v[v], pc[v], (CT)cur.yd.v[v], P.inv_d[1], yah1, ybh1, yah0, ybh0, ya1, yb1, ph.v[v], pl.v[v], xo.v[v],
-                                                psi_hi.v[v], psi_lo.v[v], xn.v[v]);
-                    lap[v] = lap[v] + t;
-                }
-                stv<T, V>(P.psi_out[1] + ypo + ld, psi_hi);
-                if (ylo_store)
-                    stv<T, V>(P.psi_out[1] + ypo, psi_lo);
-                stv<T, V>(P.xi[1] + yxo_, xn);
-            } else {
-#pragma unroll
-                for (int v = 0; v < V; ++v)
-                    lap[v] = lap[v] + d2<CT, FMA>(w2, (CT)cur.yu.v[v], pc[v], (CT)cur.yd.v[v], i2y);
-            }
-            // ---- z term, leapfrog ----------------------------------------------------------------------------------------
-            CT t[V];
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-                t[v] = d2<CT, FMA>(w2, (CT)qm.v[v], pc[v], (CT)qp.v[v], i2z);
-            if (KIND == 2 && sz > 0) {
-                const VT za = *reinterpret_cast<const VT *>(ztab + sz * 8);                 // a_h[s-1], b_h[s-1], a_h[s-2], b_h[s-2] (Float64: the first two)
-                const VT zb = *reinterpret_cast<const VT *>(ztab + sz * 8 + V);             // Float32: a[s-1], b[s-1]; Float64: a_h[s-2], b_h[s-2]
-                const T ah1 = za.v[0], bh1 = za.v[1];
-                const T ah0 = V == 4 ? za.v[V == 4 ? 2 : 0] : zb.v[0], bh0 = V == 4 ? za.v[V == 4 ? 3 : 0] : zb.v[1];
-                const T a1 = ztab[sz * 8 + 4], b1 = ztab[sz * 8 + 5];
-                const VT pl = zpl;
-                VT psi_hi = cur.ph, psi_lo = pl, xn = cur.xo;
-#pragma unroll
-                for (int v = 0; v < V; ++v)
-                    if ((okm >> v) & 1)
-                        t[v] = cd_axis_cell<T, CT>(w1, t[v], (CT)qm.v[v], pc[v], (CT)qp.v[v], P.inv_d[2], ah1, bh1, ah0, bh0, a1, b1, cur.ph.v[v], pl.v[v],
-                                                   cur.xo.v[v], psi_hi.v[v], psi_lo.v[v], xn.v[v], zhave);
-                stv<T, V>(P.psi_out[2] + col + (long long)(sz - 1) * zst, psi_hi);
-                if (k + 1 == 2 || k + 1 == nz - h + 1)
-                    stv<T, V>(P.psi_out[2] + col + (long long)(sz - 2) * zst, psi_lo);
-                stv<T, V>(P.xi[2] + col + (long long)(sz - 1) * zst, xn);
-                zcarry = psi_hi;
-                zhave = true;
-            } else if (KIND == 2)
-                zhave = false;
-            VT out = cur.po;
-#pragma unroll
-            for (int v = 0; v < V; ++v)
+            for (int v = 0; v < V; ++v) {
+                CT t = d2<CT, FMA>(w2, (CT)cur.yu.v[v], pc[v], (CT)cur.yd.v[v], i2y);
                 if ((okm >> v) & 1)
-                    out.v[v] = leapfrog<T, CT, FMA>(pc[v], cur.po.v[v], cur.fc.v[v], lap[v] + t[v]);
-            finish(k, off, out, c2, c1, c0, g);
+                    t = cd_axis_cell<T, CT>(w1, t, (CT)cur.yu.v[v], pc[v], (CT)cur.yd.v[v], P.inv_d[1], yah1, ybh1, yah0, ybh0, ya1, yb1, ph.v[v], pl.v[v], xo.v[v],
+                                            psi_hi.v[v], psi_lo.v[v], xn.v[v]);
+                lap[v] = lap[v] + t;
+            }
+            stv<T, V>(P.psi_out[1] + ypo + ld, psi_hi);
+            if (ylo_store)
+                stv<T, V>(P.psi_out[1] + ypo, psi_lo);
+            stv<T, V>(P.xi[1] + yxo_, xn);
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                lap[v] = lap[v] + d2<CT, FMA>(w2, (CT)cur.yu.v[v], pc[v], (CT)cur.yd.v[v], i2y);
         }
+        // ---- z term (plain on these planes), leapfrog ----------------------------------------------------------------------
+        VT out = cur.po;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const CT t = d2<CT, FMA>(w2, (CT)qm.v[v], pc[v], (CT)qp.v[v], i2z);
+            if ((okm >> v) & 1)
+                out.v[v] = leapfrog<T, CT, FMA>(pc[v], cur.po.v[v], cur.fc.v[v], lap[v] + t);
+        }
+        finish(k, off, out, c2, c1, c0, g);
         qm = qc;
         qc = qp;
         qp = qn;
@@ -936,13 +860,12 @@ __global__ void __launch_bounds__(CDF_RIM_T, CDF_RIMZ_MINB) cd_rimz_kernel(const
         return;
     extern __shared__ __align__(16) unsigned char cdf_smem[];
     T *xtab = reinterpret_cast<T *>(cdf_smem);
-    T *ztab = xtab + (cd_xtab_records<T, V>(P) * 5 * V + 7) / 8 * 8;
-    cd_rimz_tables<T, V>(P, xtab, ztab, false, (int)threadIdx.x, CDF_RIM_T);
+    cd_xstrip_table<T, V>(P, xtab, (int)threadIdx.x, CDF_RIM_T);
     __syncthreads();
     if (R.kind == 0)
-        cd_rimz_body<T, CT, 0, ADJ, FMA>(P, B, R, local, cta, (int)threadIdx.x, xtab, ztab);
+        cd_rimz_body<T, CT, 0, ADJ, FMA>(P, B, R, local, cta, (int)threadIdx.x, xtab);
     else
-        cd_rimz_body<T, CT, 1, ADJ, FMA>(P, B, R, local, cta, (int)threadIdx.x, xtab, ztab);
+        cd_rimz_body<T, CT, 1, ADJ, FMA>(P, B, R, local, cta, (int)threadIdx.x, xtab);
 }
 
 // Small 2D grids: both CTA kinds in one launch (the 2D bulk CTA and the rim CTA have 128 threads each).  A step of a grid that
@@ -1104,8 +1027,7 @@ void cd_fused_launch(const CdFusedParams<T> &P, const CdFusedGeom &g, bool adj, 
     const unsigned nrim = (unsigned)g.ncta_rim();
     const bool f32fast = sizeof(T) == 4 && fast, has_y = g.has_y;
     // x-strip coefficient table of the marching rim kernel: one record of 5 V values per strip vector
-    // + one record of 8 values per z strip index
-    const size_t rimz_smem = (((size_t)(g.ivlo + ((int)(cdf_ld(g.nx, sizeof(T)) / g.v) - g.ivhi)) * 5 * g.v + 7) / 8 * 8 + (size_t)(2 * P.halo + 1) * 8) * sizeof(T);
+    const size_t rimz_smem = (size_t)(g.ivlo + ((int)(cdf_ld(g.nx, sizeof(T)) / g.v) - g.ivhi)) * 5 * g.v * sizeof(T);
     if (merged && !has_y && g.gx > 0 && nrim > 0) {
         const int nbulk = g.gx * g.gz;
 #define SWB_CDF_M(CT, AD, FM)                                                                            \

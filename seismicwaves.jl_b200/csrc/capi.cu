@@ -1,5 +1,7 @@
 // capi.cu -- the extern "C" surface declared in include/swb200.h.
 #include "engine.h"
+#include "cd_fused.h"
+#include <unordered_set>
 #include <dlfcn.h>
 #include <nccl.h>
 #include <cstring>
@@ -39,6 +41,49 @@ int32_t swb_device_count(void)
 }
 
 int64_t swb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int32_t swb_diag_cd_partition(int32_t esize, int32_t nx, int32_t ny, int32_t nz, int32_t halo, int32_t zc, int32_t zpml_lo, int32_t zpml_hi,
+                              int32_t rim_zc, int64_t *counts)
+{
+    SWB_API_BEGIN
+    SWB_REQUIRE((esize == 4 || esize == 8) && nx >= 3 && ny >= 1 && nz >= 3 && halo >= 0 && zc >= 1 && counts != nullptr, "bad arguments");
+    const bool has_y = ny > 1;
+    const CdFusedGeom g = cd_fused_geom((size_t)esize, nx, ny, nz, halo, has_y, zc, zpml_lo != 0, zpml_hi != 0, rim_zc < 0 ? CDF_RIM_ZC : rim_zc);
+    counts[0] = counts[1] = counts[2] = 0;
+    std::unordered_set<unsigned long long> seen;
+    seen.reserve((size_t)nx * ny * nz * 2);
+    const long long bulk_slots = (long long)g.zc * g.ty * g.tx, vec_slots = (long long)CDF_RIM_T * g.v;
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                int cta = -1, code = -1;
+                const int which = cd_fused_locate(g, i, j, k, &cta, &code);
+                long long slots;
+                int kind;
+                if (which == 0) {
+                    SWB_REQUIRE(cta >= 0 && cta < g.ncta_bulk(), "bulk CTA out of range");
+                    slots = bulk_slots, kind = 0;
+                } else {
+                    SWB_REQUIRE(cta >= 0 && cta < g.ncta_rim(), "rim CTA out of range");
+                    const bool marched = g.rim_zc > 0 && cta < g.nrimz_cta;
+                    kind = marched ? 1 : 2;
+                    slots = vec_slots;
+                    if (marched) { // the chunk length of the box this CTA belongs to
+                        int b = g.nbox_v;
+                        for (int q = g.nbox_v + 1; q < g.nbox; ++q)
+                            if (cta >= g.rt[q].cta0)
+                                b = q;
+                        slots = (long long)g.rt[b].zc * vec_slots;
+                    }
+                }
+                SWB_REQUIRE(code >= 0 && code < slots, "in-CTA slot out of range");
+                const unsigned long long key = ((unsigned long long)which << 62) | ((unsigned long long)cta << 26) | (unsigned long long)code;
+                SWB_REQUIRE(code < (1 << 26), "slot does not fit the check's key");
+                SWB_REQUIRE(seen.insert(key).second, "two cells share one (kernel, CTA, slot)");
+                counts[kind]++;
+            }
+    SWB_API_END
+}
 
 // ---- 1. device buffers --------------------------------------------------------------------------
 int32_t swb_set_device(int32_t device)

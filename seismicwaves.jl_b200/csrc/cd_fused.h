@@ -8,6 +8,7 @@ constexpr int CDF_TY = 8;      // rows of a 3D bulk tile (one warp per row)
 constexpr int CDF_W2D = 4;     // warps per CTA in the 2D bulk variant (each warp owns its own x range)
 constexpr int CDF_RIM_T = 128; // threads (= vectors) per CTA of the rim kernel
 constexpr int CDF_MAX_BOX = 6;
+constexpr int CDF_RIM_ZC = 16; // planes per chunk of the 3D rim march (engine default; SWB_CDF_RIM_ZC overrides, 0 = per-vector rim kernel only)
 
 // elements per 16-byte vector and cells per warp-row
 inline int cdf_vec(size_t esize) { return (int)(16 / esize); }

@@ -164,3 +164,30 @@ def test_header_is_valid_c_and_layout_matches_a_c_compiler(tmp_path):
     out = subprocess.check_output([str(exe)], text=True)
     sizes = dict((ln.split()[0], int(ln.split()[1])) for ln in out.splitlines())
     assert sizes == {k: v["size"] for k, v in layout.items()}
+
+
+@pytest.mark.parametrize("esize", [4, 8])
+def test_fused_cd_kernels_partition_the_grid(esize):
+    """The fused CD step (csrc/acou_cd_fused.cu) runs a grid as up to three launches that write disjoint cells -- the bulk march,
+    the z-marched x / y strip boxes, the per-vector strips / faces -- and addresses sources / receivers as (kernel, CTA, slot).
+    Host-only check through the C ABI (no device): every cell of a grid is owned exactly once and every slot lies inside its CTA,
+    for 2D and 3D shapes, odd extents, every strip combination of the z ends (free surface, z-slab interior faces), with and
+    without the march."""
+    import swb200 as S
+
+    lib = S._lib.load()
+    counts = (C.c_int64 * 3)()
+    v = 16 // esize
+    shapes = [(37, 1, 29, 4), (300, 1, 280, 20), (131, 1, 64, 0),  # 2D (ny = 1)
+              (40, 36, 44, 6), (70, 52, 90, 8), (129, 33, 47, 5), (64, 40, 61, 10), (48, 48, 48, 0), (260, 30, 33, 12), (33, 31, 30, 14)]
+    for nx, ny, nz, halo in shapes:
+        for zlo, zhi in [(1, 1), (0, 1), (1, 0), (0, 0)]:
+            for rim_zc in (-1, 0, 5):
+                for zc in (7, 64):
+                    rc = lib.swb_diag_cd_partition(esize, nx, ny, nz, halo, zc, zlo, zhi, rim_zc, counts)
+                    assert rc == 0, (nx, ny, nz, halo, zlo, zhi, rim_zc, zc, lib.swb_last_error())
+                    assert sum(counts) == nx * ny * nz
+                    marched_possible = ny > 1 and rim_zc != 0 and nx >= 2 * halo + v
+                    assert (counts[1] > 0) == (marched_possible and ny > 2), (nx, ny, nz, halo, zlo, zhi, rim_zc, list(counts))
+                    if halo > 0 and nx > 2 * halo + 2 * v + 8 and nz > 2 * halo + 4 and (ny == 1 or ny > 2 * halo + 2):
+                        assert counts[0] > 0  # a bulk exists
