@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "seismicwaves.jl_b200", "libswb200.so")
-KEYS = ["UTMALDG", "SYNCS", "SHFL", "LDG.E.128", "STG.E.128", "LDS.128", "STS.128", "F2F", "DFMA", "FFMA", "HMMA", "UTCMMA", "BAR.SYNC"]
+KEYS = ["UTMALDG", "SYNCS", "SHFL", "LDG.E.128", "STG.E.128", "LDS.128", "STS.128", "F2F", "DFMA", "FFMA", "HMMA", "UTCMMA", "BAR.SYNC", "PREEXIT", "ACQBULK"]  # PREEXIT / ACQBULK = griddepcontrol.launch_dependents / .wait (programmatic dependent launch)
 
 
 def main():
