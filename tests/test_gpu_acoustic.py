@@ -329,6 +329,33 @@ def test_cd_fused_points_on_faces_and_fast_f32():
     assert rel_l2(ggot["vp"], gref["vp"]) <= tol(np.float32)
 
 
+@pytest.mark.parametrize("freetop", [True, False])
+def test_cd3d_fused_points_inside_the_rim_boxes(freetop):
+    """3D: sources / receivers inside the C-PML strips -- the cells of the z-marched x / y strip boxes, of their corner columns and of
+    the per-vector z planes -- reach the kernels through per-CTA lists whose numbering differs per rim form: the fused engine must
+    agree bit for bit with the one-launch-per-reference-kernel path (which has no such lists), and with the oracle"""
+    n, halo = (70, 45, 80), 6
+    case = acoustic_case(kind="acoustic_cd", n=n, nt=140, halo=halo, dtype=np.float32, seed=12, nshots=1, nsrc=3, nrec=12, freetop=freetop)
+    h = case["h"]
+    idx = [(2, 20, 40), (66, 22, 30), (35, 3, 50), (30, 41, 20), (2, 2, 41), (67, 42, 60), (33, 21, 76), (3, 3, 77), (34, 20, 79), (0, 10, 33), (40, 44, 35), (36, 2, 3)]
+    for r, (i, j, k) in enumerate(idx):  # x strips, y strips, x-y corner columns, the lower z strip and its corners, faces, the top planes
+        case["shots"][0]["rec_positions"][r, :] = (i * h, j * h, k * h)
+    case["shots"][0]["src_positions"][1, :] = (30 * h, 4 * h, 45 * h)   # a source inside a y strip
+    case["shots"][0]["src_positions"][2, :] = (64 * h, 25 * h, 38 * h)  # and one inside an x strip
+    a, _ = _forward_product(case, fused=True)
+    b, _ = _forward_product(case, fused=False)
+    assert np.array_equal(a[0], b[0])
+    assert np.count_nonzero(np.abs(a[0]).max(axis=0) > 0) >= 9  # the strip receivers see the wavefield (faces stay zero)
+    ref, _ = oracle_forward(case)
+    assert rel_l2(a[0], ref[0]) <= 1e-6
+    observed = make_observed(case, ref)
+    for cf in (1, 7):
+        (ga, ma), _ = _gradient_product(case, observed, check_freq=cf, fused=True)
+        (gb, mb), _ = _gradient_product(case, observed, check_freq=cf, fused=False)
+        assert np.array_equal(ga["vp"], gb["vp"]), cf
+        assert ma == mb
+
+
 @pytest.mark.parametrize("kind,n", [("acoustic_vd", (300, 170)), ("acoustic_cd", (300, 170)), ("acoustic_cd", (70, 45, 80))])
 def test_eager_launches_equal_graph_replay(kind, n):
     """SWB_FLAG_NO_GRAPH: the same launch sequence enqueued eagerly (two shots: the second one replays the captured graphs)"""
