@@ -46,20 +46,6 @@ struct alignas(16) Chunk {
     T v[4];
 };
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-template <class T>
-__device__ __forceinline__ void cp_async_chunk(T *smem, const T *gmem)
-{
-    cp_async16(smem, gmem);
-    if (sizeof(T) == 8)
-        cp_async16((char *)smem + 16, (const char *)gmem + 16);
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
 template <class T>
 __device__ __forceinline__ Chunk<T> ldg_chunk(const T *p)
 {
@@ -80,8 +66,8 @@ __device__ __forceinline__ CT fd4(const VdFusedParams<T> &P, T fm1, T f0, T f1, 
     return acc * (CT)inv;
 }
 
-// smem layout (elements of T); every input of the tile is staged with cp.async so that a CTA has its whole
-// working set (~57 KB in Float32) in flight at once -- the SM keeps HBM busy with 3 resident CTAs instead of
+// smem layout (elements of T); every input of the tile is staged by TMA so that a CTA has its whole
+// working set (~50 KB in Float32) in flight at once -- the SM keeps HBM busy with 3-4 resident CTAs instead of
 // depending on per-thread load/use latency.
 template <class T, int TY, bool ADJ>
 struct VdSmem {
@@ -138,22 +124,6 @@ __device__ __forceinline__ void vd_stage_wait(T *sm)
 {
     __syncthreads(); // (the mbarrier's initialisation becomes visible to the waiting threads)
     mbar_wait(reinterpret_cast<unsigned long long *>(sm + VdSmem<T, TY, ADJ>::BAR_OFF), 0);
-}
-
-// stage `nrows` rows of chunks [c0, c1) (chunk 0 = global column gx0) from a padded plane into shared memory
-template <class T>
-__device__ __forceinline__ void stage_rows(T *dst, int dstride, const T *src_row0, long long ld, int gx0, int nrows, int c0, int c1, int tid)
-{
-    const int ncs = c1 - c0;
-    for (int idx = tid; idx < nrows * ncs; idx += NTHR) {
-        const int r = idx / ncs, c = c0 + (idx - r * ncs);
-        T *d = dst + r * dstride + 4 * c;
-        if (gx0 + 4 * c >= ld) { // beyond the row pitch: only feeds cells that are never stored
-            Chunk<T> z = {};
-            st_chunk(d, z);
-        } else
-            cp_async_chunk(d, src_row0 + (long long)r * ld + 4 * c);
-    }
 }
 
 // ---- chunk bodies of the edge tiles.  SPC = true: the reference's range tests and C-PML per cell; SPC = false: the chunk lies
@@ -586,8 +556,6 @@ __device__ __forceinline__ void vd_tile_interior(const VdFusedParams<T> &P, unsi
     const long long ld = P.ld;
     const int tile = trow * gridDim.x + blockIdx.x;
     const long long o = (long long)y0 * ld + x0 + 4 * lane; // this lane's chunk in row 0 of the tile
-    // lanes 0..3 additionally fetch the halo chunks -2, -1, NCH, NCH+1 of a row
-    const int hc = lane < 2 ? lane - 2 - lane : NCH + (lane - 2) - lane; // chunk offset relative to this lane's own chunk
 
     // ---- phase 1: everything the tile needs goes into shared memory (TMA), m0 straight to registers ---------
     vd_stage_tma_material<T, TY, ADJ>(P, sm, x0, y0);
