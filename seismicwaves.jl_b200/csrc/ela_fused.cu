@@ -638,7 +638,7 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
         tma_load_2d(S.sxx, &P.tm[2], x0 - 4, ys, &S.bar);
         tma_load_2d(S.szz, &P.tm[3], x0 - 4, ys, &S.bar);
         tma_load_2d(S.sxz, &P.tm[4], x0 - 4, ys, &S.bar);
-        if (ADJ) {
+        if constexpr (ADJ) {
             tma_load_2d(S.fx, &P.tm[5], x0 - 4, ys, &S.bar);
             tma_load_2d(S.fz, &P.tm[6], x0 - 4, ys, &S.bar);
         }
@@ -647,7 +647,7 @@ __device__ __forceinline__ void ela_tile(const ElaFusedParams<T> &P, ElaSmem<T, 
         tma_load_2d(S.sxx + SH1 * W, &P.tm[7], x0 - 4, ys + SH1, &S.bar2);
         tma_load_2d(S.szz + SH1 * W, &P.tm[8], x0 - 4, ys + SH1, &S.bar2);
         tma_load_2d(S.sxz + SH1 * W, &P.tm[9], x0 - 4, ys + SH1, &S.bar2);
-        if (ADJ) {
+        if constexpr (ADJ) {
             tma_load_2d(S.fx + SH1 * W, &P.tm[10], x0 - 4, ys + SH1, &S.bar2);
             tma_load_2d(S.fz + SH1 * W, &P.tm[11], x0 - 4, ys + SH1, &S.bar2);
         }
