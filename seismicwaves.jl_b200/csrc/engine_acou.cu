@@ -250,11 +250,9 @@ class AcousticCD : public SimBase {
         tic();
         cd_step(a, record);
         toc();
-        void *o = cur_[0];
         cur_[0] = cur_[1];
         cur_[1] = cur_[2];
         cur_[2] = cur_[0]; // pnew aliases pold from now on, as in the reference
-        (void)o;
         cell_updates += (int64_t)ncells();
     }
 
