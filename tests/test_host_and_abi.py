@@ -191,3 +191,23 @@ def test_fused_cd_kernels_partition_the_grid(esize):
                     assert (counts[1] > 0) == (marched_possible and ny > 2), (nx, ny, nz, halo, zlo, zhi, rim_zc, list(counts))
                     if halo > 0 and nx > 2 * halo + 2 * v + 8 and nz > 2 * halo + 4 and (ny == 1 or ny > 2 * halo + 2):
                         assert counts[0] > 0  # a bulk exists
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the B200 arm) needs no GPU: it must print one JSON line with
+    the contract's keys -- the B200 arm's metric / unit / config, `impl`, a `cpu_baseline` describing the run and an `e2e` block
+    that repeats the value with zero host <-> device bytes."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"].startswith("Gcell-updates/s") and line["unit"] == "Gcell-updates/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["value"] > 0
+    assert line["config"]["workload"].startswith("C2:") and line["dtype"] == "f32" and line["data"] == "synthetic"
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == line["value"] and "4096x4096" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
